@@ -1,0 +1,90 @@
+// aux_kernels.cu -- K5 (LUT accumulator generation), K6 (key conversion), trivial ciphertexts and the
+// DFMA peak microbenchmark, for sm_100a.
+#include "kernels.cuh"
+
+namespace fhestr {
+
+// ---- K5: 16-entry function table -> body polynomial of the trivial GLWE accumulator:
+// boxes of N/16 coefficients f(i) << delta_log, first half-box negated, rotated left by half a box.
+// Replaces shortint generate_lookup_table (used by every op of fheasciichar.rs:35-104).
+__global__ void lut_poly_kernel(const uint8_t* table, int entries, int delta_log, u64* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kN) return;
+    const int box = kN / entries;
+    const int m = (j + box / 2) & (kN - 1);
+    const u64 v = ((u64)table[m / box]) << delta_log;
+    out[j] = (m < box / 2) ? (u64)0 - v : v;
+}
+int launch_lut_poly(const uint8_t* table_dev, int entries, int delta_log, u64* out, cudaStream_t s) {
+    lut_poly_kernel<<<kN / 256, 256, 0, s>>>(table_dev, entries, delta_log, out);
+    return 1;
+}
+
+// ---- K6: standard-domain GGSW polynomials -> Fourier BSK in the engine layout.  One warp per
+// polynomial, same forward transform as the blind rotation (br_core.cuh: bsk_poly_forward).
+struct ConvCtx {
+    int lane_;
+    double* xbuf_;
+    __device__ __forceinline__ int lane() const { return lane_; }
+    __device__ __forceinline__ double* xbuf() { return xbuf_; }
+    __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+    __device__ __forceinline__ cplx ldg(const cplx* p) const {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+        return cplx{v.x, v.y};
+    }
+};
+__global__ void __launch_bounds__(128) bsk_convert_kernel(const u64* bsk_std, int n_polys, const cplx* tf, cplx* out) {
+    __shared__ __align__(16) double xb[4][kXbufDoubles];
+    const int warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * 4 + warp;  // polynomial index = (step*2 + row)*2 + col
+    if (q >= n_polys) return;
+    ConvCtx c{(int)(threadIdx.x & 31), xb[warp]};
+    const int step = q >> 2, row = (q >> 1) & 1, col = q & 1;
+    bsk_poly_forward(c, bsk_std + (size_t)q * kN, out + (size_t)step * kBskStepElems, row, col, tf);
+}
+int launch_bsk_convert(const u64* bsk_std, int n, const cplx* tf, cplx* out, cudaStream_t s) {
+    const int polys = n * 4;
+    bsk_convert_kernel<<<(polys + 3) / 4, 128, 0, s>>>(bsk_std, polys, tf, out);
+    return 1;
+}
+
+// ---- trivial ciphertexts: mask 0, body value << delta_log (create_trivial_radix, fheasciichar.rs:23)
+__global__ void trivial_kernel(u64* arena, uint32_t first, uint32_t count, const uint8_t* values, int delta_log) {
+    const uint32_t b = blockIdx.x;
+    if (b >= count) return;
+    u64* ct = arena + (size_t)(first + b) * (kN + 1);
+    for (int idx = threadIdx.x; idx <= kN; idx += blockDim.x)
+        ct[idx] = (idx == kN) ? ((u64)values[b]) << delta_log : 0ull;
+}
+int launch_trivial(u64* arena, uint32_t first, uint32_t count, const uint8_t* values_dev, int delta_log, cudaStream_t s) {
+    if (!count) return 0;
+    trivial_kernel<<<count, 256, 0, s>>>(arena, first, count, values_dev, delta_log);
+    return 1;
+}
+
+// ---- DFMA peak: 16 independent FMA chains per thread, 8 warps x 4 CTAs per SM
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double m = 1.0000000001, c = 1e-12;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == 123.456) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int launch_dfma_peak(double* sink, int iters, unsigned long long* fmas, cudaStream_t s) {
+    const int grid = 148 * 8, block = 256;
+    dfma_peak_kernel<<<grid, block, 0, s>>>(sink, iters);
+    *fmas = (unsigned long long)grid * block * (unsigned long long)iters * 8ull * 16ull;
+    return 1;
+}
+
+}  // namespace fhestr

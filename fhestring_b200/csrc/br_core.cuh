@@ -1,0 +1,280 @@
+// br_core.cuh -- per-thread body of the blind-rotation CMUX step (GGSW x GLWE external product with a
+// register/shared-memory negacyclic f64 FFT), written once and compiled twice:
+//   * by nvcc into the sm_100a kernel (blind_rotate.cu), Ctx = device warp context;
+//   * by g++ into the host emulation used by the CPU tests (tests/emu/br_emu.cpp), Ctx = std::thread
+//     + std::barrier context, so the exact index logic is checked against the oracle without a GPU.
+//
+// Replaces (reference side): the tfhe-rs blind rotation behind every PBS issued from
+// /root/reference/src/ciphertext/fheasciichar.rs:36-102.
+//
+// Geometry.  N = 2048, k = 1, one decomposition level of 23 bits.  A polynomial p is folded to M = 1024
+// complex points c_n = p_n + i p_{n+M}; its negacyclic spectrum is X_k = sum_n c_n zeta^n W^{nk},
+// zeta = exp(i pi / N), W = exp(-2 pi i / M)  (so X_k = p(y_k), y_k = exp(i pi (1-4k)/N), y_k^N = -1).
+// Four-step 32 x 32:  n = 32 n1 + n2,  k = k1 + 32 k2.
+//   pass 1 (lane = n2, registers n1 -> k1): merged-twist 32-point transform (fft32_fwd_p1)
+//   twiddle Tf(k1,n2) = exp(i pi n2 (1-4 k1)/N), transpose through shared memory
+//   pass 2 (lane = k1, registers n2 -> k2): plain DFT-32 (fft32_fwd_p2)
+// ONE WARP owns one polynomial: 32 complex points per lane live in registers, the only exchange inside
+// a transform is one 32x32 transpose (done as two 8-byte halves through an 8.25 KB padded buffer), and
+// only __syncwarp is needed.  The two warps of a PBS (mask polynomial, body polynomial) swap one
+// spectrum per step through the same buffers (pair barrier).  The inverse mirrors the forward and ends
+// in the layout the next step's forward starts from, so the new accumulator words stay in registers.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FHE_HD __host__ __device__ __forceinline__
+#else
+#define FHE_HD inline
+#endif
+#include "fft32_gen.cuh"
+
+namespace fhestr {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr int kN = 2048;          // polynomial size
+constexpr int kM = 1024;          // complex points
+constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-free 64-bit column reads
+constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B per warp
+constexpr int kPbsBaseLog = 23;
+
+struct alignas(16) cplx { double x, y; };
+
+FHE_HD cplx cmul(cplx a, cplx b) {
+    cplx r;
+    r.x = fma(a.x, b.x, -(a.y * b.y));
+    r.y = fma(a.x, b.y, a.y * b.x);
+    return r;
+}
+
+// A.6 modulus switch to 2N = 4096, reduced to [0, 2N)
+FHE_HD uint32_t modswitch_2N(u64 x) {
+    u64 t = x >> (64 - 12 - 1);
+    t += t & 1;
+    t >>= 1;
+    return (uint32_t)t & (2 * kN - 1);
+}
+
+// A.4 signed decomposition, one level of 23 bits: digit in (-2^22, 2^22]
+FHE_HD double digit23(u64 x) {
+    const uint32_t hi = (uint32_t)((x + (1ull << 40)) >> 32);
+    int32_t d = ((int32_t)hi) >> 9;
+    if (d == -(1 << 22)) d = (1 << 22);
+    return (double)d;
+}
+
+// coefficient j of X^e * P (negacyclic), e in [0, 2N)
+FHE_HD u64 rot_coef(const u64* P, int j, int e) {
+    const int q = (j - e) & (2 * kN - 1);
+    const u64 v = P[q & (kN - 1)];
+    return (q & kN) ? (u64)0 - v : v;
+}
+
+// x in torus turns -> round(frac(x) * 2^64) as a wrapping u64
+FHE_HD u64 torus_from_double(double x) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: (x + magic) - magic == rint(x) for |x| < 2^51
+    const double r = (x + magic) - magic;
+    const double f = (x - r) * 18446744073709551616.0;
+#ifdef __CUDA_ARCH__
+    return (u64)__double2ll_rn(f);
+#else
+    return (u64)(i64)llrint(f);
+#endif
+}
+
+// 32x32 transpose of one double per (lane, register) through the warp's padded buffer
+template <class Ctx>
+FHE_HD void transpose32(Ctx& c, double (&v)[32]) {
+    const int t = c.lane();
+    double* buf = c.xbuf();
+#pragma unroll
+    for (int r = 0; r < 32; r++) buf[r * kXPad + t] = v[r];
+    c.syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; r++) v[r] = buf[t * kXPad + r];
+    c.syncwarp();
+}
+
+// forward transform of the 32 complex points held by this lane (lane = n2, register n1) into the
+// spectrum layout (lane = k1, register k2).  tf[k1*32 + n2].
+template <class Ctx>
+FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* tf) {
+    const int t = c.lane();
+    fft32_fwd_p1(re, im);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+        const cplx w = c.ldg(tf + k1 * 32 + t);
+        const cplx z = cmul(cplx{re[k1], im[k1]}, w);
+        re[k1] = z.x; im[k1] = z.y;
+    }
+    transpose32(c, re);
+    transpose32(c, im);
+    fft32_fwd_p2(re, im);
+}
+
+// inverse: (lane = k1, register k2) -> (lane = n2, register n1).  ti[n2*32 + k1] = conj(Tf(k1,n2)).
+template <class Ctx>
+FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* ti) {
+    const int t = c.lane();
+    fft32_inv_p1(re, im);
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) {
+        const cplx w = c.ldg(ti + n2 * 32 + t);
+        const cplx z = cmul(cplx{re[n2], im[n2]}, w);
+        re[n2] = z.x; im[n2] = z.y;
+    }
+    transpose32(c, re);
+    transpose32(c, im);
+    fft32_inv_p2(re, im);
+}
+
+// Fourier BSK layout (engine-private, produced once by the key-conversion kernel):
+//   g[ ((((step*2 + row)*32 + k2)*2 + col)*32 + k1 ]   complex f64, k = k1 + 32 k2
+// scaled by 2^-64 / M so that the inverse transform directly yields torus turns.
+constexpr int kBskStepElems = 2 * 32 * 2 * 32;  // 4096 complex = 64 KiB per CMUX step
+FHE_HD int bsk_index(int row, int k2, int col, int k1) { return ((row * 32 + k2) * 2 + col) * 32 + k1; }
+
+// One CMUX step for this warp's polynomial:  ACC += GGSW (x) (X^e * ACC - ACC).
+//   a[0..31]  = ACC[32 n1 + lane], a[32..63] = ACC[32 n1 + lane + M]  (registers, in/out)
+//   c.acc()   = this polynomial's accumulator in shared memory (same values), updated on exit
+template <class Ctx>
+FHE_HD void cmux_step(Ctx& c, u64 (&a)[64], int e, const cplx* g, const cplx* tf, const cplx* ti) {
+    const int t = c.lane();
+    const int p = c.poly();
+    u64* acc = c.acc();
+    double re[32], im[32];
+    // rotate, subtract, decompose
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        const int j = 32 * n1 + t;
+        re[n1] = digit23(rot_coef(acc, j, e) - a[n1]);
+        im[n1] = digit23(rot_coef(acc, j + kM, e) - a[32 + n1]);
+    }
+    forward1024(c, re, im, tf);
+    // Fourier-domain GGSW product; the partner warp receives our contribution to ITS output
+    // polynomial, 16 spectrum rows at a time, through our transpose buffer
+    cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
+    const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int k2 = half * 16 + q;
+            const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
+            const cplx go = c.ldg(g + bsk_index(p, k2, 1 - p, t));
+            const cplx d = cplx{re[k2], im[k2]};
+            xo[q * 32 + t] = cmul(d, go);
+            const cplx s = cmul(d, gs);
+            re[k2] = s.x; im[k2] = s.y;
+        }
+        c.pair_sync();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int k2 = half * 16 + q;
+            const cplx v = xp[q * 32 + t];
+            re[k2] += v.x; im[k2] += v.y;
+        }
+        c.pair_sync();
+    }
+    inverse1024(c, re, im, ti);
+    // accumulate into the torus accumulator; keep the new words in registers for the next step
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        const int j = 32 * n1 + t;
+        a[n1] = acc[j] + torus_from_double(re[n1]);
+        a[32 + n1] = acc[j + kM] + torus_from_double(im[n1]);
+        acc[j] = a[n1];
+        acc[j + kM] = a[32 + n1];
+    }
+    c.syncwarp();
+}
+
+// Forward transform of one standard-domain GGSW polynomial (key conversion, once per key)
+template <class Ctx>
+FHE_HD void bsk_poly_forward(Ctx& c, const u64* poly, cplx* out_step, int row, int col, const cplx* tf) {
+    const int t = c.lane();
+    const double sc = 1.0 / (18446744073709551616.0 * (double)kM);
+    double re[32], im[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        const int j = 32 * n1 + t;
+        re[n1] = (double)(i64)poly[j] * sc;
+        im[n1] = (double)(i64)poly[j + kM] * sc;
+    }
+    forward1024(c, re, im, tf);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; k2++) out_step[bsk_index(row, k2, col, t)] = cplx{re[k2], im[k2]};
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole blind rotation for one PBS, executed by a pair of warps (poly 0 = mask, poly 1 = body).
+// Fuses the modulus switch (A.6) in front and the sample extraction (A.8) behind.
+struct BrJobView {
+    const u64* ks;        // [n+1] keyswitched LWE (small key), u64
+    const u64* lut;       // [N] body polynomial of the trivial GLWE accumulator
+    const u64* init_acc;  // optional [2][N]: start from this GLWE instead of X^{-b~} * LUT (test hook)
+    u64* out_lwe;         // optional [N+1]: sample-extracted LWE under the big key
+    u64* out_acc;         // optional [2][N]: raw accumulator (test hook)
+    int n;                // number of CMUX steps (small LWE dimension)
+};
+
+template <class Ctx>
+FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const cplx* tf, const cplx* ti) {
+    const int t = c.lane();
+    const int p = c.poly();
+    const int n = job.n;
+    uint16_t* at = c.atilde();
+    for (int idx = p * 32 + t; idx <= n; idx += 64) at[idx] = (uint16_t)modswitch_2N(job.ks[idx]);
+    c.pair_sync();
+    u64* acc = c.acc();
+    u64 a[64];
+    {
+        const int e0 = (2 * kN - (int)at[n]) & (2 * kN - 1);
+#pragma unroll
+        for (int m = 0; m < 64; m++) {
+            const int j = 32 * m + t;  // m < 32: j = 32 n1 + t ; m >= 32: j = 32 n1 + t + M
+            u64 v;
+            if (job.init_acc) v = job.init_acc[p * kN + j];
+            else v = (p == 1) ? rot_coef(job.lut, j, e0) : (u64)0;
+            a[m] = v;
+            acc[j] = v;
+        }
+    }
+    c.syncwarp();
+    for (int i = 0; i < n; i++) {
+        const int e = at[i];
+        if (e == 0) continue;  // X^0 * ACC - ACC == 0: the external product contributes exactly nothing
+        cmux_step(c, a, e, bsk + (size_t)i * kBskStepElems, tf, ti);
+    }
+    if (job.out_acc) {
+#pragma unroll
+        for (int m = 0; m < 64; m++) job.out_acc[p * kN + 32 * m + t] = a[m];
+    }
+    if (job.out_lwe) {
+        if (p == 0) {
+#pragma unroll
+            for (int m = 0; m < 64; m++) {
+                const int j = 32 * m + t;
+                job.out_lwe[j] = (j == 0) ? acc[0] : (u64)0 - acc[kN - j];
+            }
+        } else if (t == 0) {
+            job.out_lwe[kN] = acc[0];
+        }
+    }
+}
+
+// Twiddle tables shared by the engine and the host emulation:
+//   tf[k1*32 + n2] = exp(+i pi n2 (1-4 k1) / N),  ti[n2*32 + k1] = conj of the same value
+inline void make_twiddles(cplx* tf, cplx* ti) {
+    for (int k1 = 0; k1 < 32; k1++)
+        for (int n2 = 0; n2 < 32; n2++) {
+            const long double ang = 3.14159265358979323846264338327950288L * (long double)(n2 * (1 - 4 * k1)) / (long double)kN;
+            const double cr = (double)cosl(ang), ci = (double)sinl(ang);
+            tf[k1 * 32 + n2] = cplx{cr, ci};
+            ti[n2 * 32 + k1] = cplx{cr, -ci};
+        }
+}
+
+}  // namespace fhestr

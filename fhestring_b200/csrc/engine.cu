@@ -1,0 +1,462 @@
+// engine.cu -- the C ABI of libfhestr_engine.so (include/fhestr_engine.h): device-resident key store,
+// ciphertext arena, LUT registry and the batched-PBS launch path.  No CPU fallback anywhere: if CUDA
+// is not usable every entry point fails with an error code.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace fhestr;
+
+static thread_local std::string g_create_error;
+
+struct fhestr_engine {
+    fhestr_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    u64* arena = nullptr;
+    uint64_t arena_blocks = 0;
+    bool own_arena = false;
+    cplx* bsk_f = nullptr;
+    u64* ksk = nullptr;
+    u64* ksk_corr = nullptr;
+    cplx* tf = nullptr;
+    cplx* ti = nullptr;
+    bool keys_loaded = false;
+    u64* luts = nullptr;
+    int n_luts = 0, cap_luts = 256;
+    // per-batch scratch (grown on demand)
+    fhestr_job* d_jobs = nullptr;
+    size_t jobs_cap = 0;
+    u64* ks_out = nullptr;
+    size_t ks_cap = 0;
+    uint8_t* d_bytes = nullptr;
+    size_t bytes_cap = 0;
+    int pbs_per_cta = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+struct fhestr_program {
+    fhestr_engine* eng = nullptr;
+    fhestr_job* d_jobs = nullptr;          // all jobs, PBS jobs of a level first, then its leveled jobs
+    std::vector<uint32_t> level_off;       // n_levels + 1
+    std::vector<uint32_t> level_pbs;       // PBS jobs in each level (the rest are leveled)
+    uint32_t max_level_pbs = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            char _b[512];                                                                          \
+            snprintf(_b, sizeof _b, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                     cudaGetErrorString(_e));                                                      \
+            e->err = _b;                                                                           \
+            return FHESTR_E_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+static int fail(fhestr_engine* e, int code, const std::string& msg) {
+    e->err = msg;
+    return code;
+}
+
+static int ensure_scratch(fhestr_engine* e, size_t n_jobs) {
+    if (n_jobs > e->jobs_cap) {
+        if (e->d_jobs) CK(cudaFree(e->d_jobs));
+        e->jobs_cap = n_jobs * 2 + 64;
+        CK(cudaMalloc(&e->d_jobs, e->jobs_cap * sizeof(fhestr_job)));
+    }
+    if (n_jobs > e->ks_cap) {
+        if (e->ks_out) CK(cudaFree(e->ks_out));
+        e->ks_cap = n_jobs * 2 + 64;
+        CK(cudaMalloc(&e->ks_out, e->ks_cap * (size_t)(e->prm.n + 1) * sizeof(u64)));
+    }
+    return FHESTR_OK;
+}
+
+static int validate_jobs(fhestr_engine* e, const fhestr_job* jobs, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        const fhestr_job& j = jobs[i];
+        if (j.n_terms > FHESTR_MAX_TERMS) return fail(e, FHESTR_E_INVALID, "job has too many terms");
+        if (j.dst >= e->arena_blocks) return fail(e, FHESTR_E_INVALID, "job dst outside the arena");
+        if (j.lut >= e->n_luts) return fail(e, FHESTR_E_INVALID, "job uses an unregistered LUT");
+        for (uint32_t t = 0; t < j.n_terms; t++)
+            if (j.src[t] >= e->arena_blocks) return fail(e, FHESTR_E_INVALID, "job src outside the arena");
+    }
+    return FHESTR_OK;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* fhestr_last_error(const fhestr_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_blocks, void* external_arena,
+                         fhestr_engine** out) {
+    if (!p || !out) { g_create_error = "null argument"; return FHESTR_E_INVALID; }
+    *out = nullptr;
+    if (p->N != kN || p->k != 1 || p->pbs_level != 1 || p->pbs_base_log != kPbsBaseLog || p->n < 1 ||
+        p->n > 767 || p->ks_level < 1 || p->ks_level > 8 || p->ks_base_log < 1 ||
+        (p->ks_base_log + 1) * p->ks_level > 32 || p->delta_log < 48 || p->delta_log > 62) {
+        g_create_error = "unsupported parameter set (need N=2048, k=1, pbs 1x23 bits, n<=767, (ks_base_log+1)*ks_level<=32)";
+        return FHESTR_E_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        g_create_error = "no usable CUDA device (this engine has no CPU fallback)";
+        return FHESTR_E_NOGPU;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100-class; the kernels are built for sm_100a only";
+        return FHESTR_E_NOGPU;
+    }
+    fhestr_engine* e = new (std::nothrow) fhestr_engine();
+    if (!e) { g_create_error = "out of host memory"; return FHESTR_E_STATE; }
+    e->prm = *p;
+    e->device = device;
+    e->arena_blocks = arena_blocks;
+    auto bail = [&](int code) { g_create_error = e->err; fhestr_engine_destroy(e); return code; };
+#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { e->err = std::string(#call) + ": " + cudaGetErrorString(_e); return bail(FHESTR_E_CUDA); } } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    if (external_arena) e->arena = static_cast<u64*>(external_arena);
+    else {
+        CKC(cudaMalloc(&e->arena, arena_blocks * (size_t)(kN + 1) * sizeof(u64)));
+        e->own_arena = true;
+        CKC(cudaMemsetAsync(e->arena, 0, arena_blocks * (size_t)(kN + 1) * sizeof(u64), e->stream));
+    }
+    CKC(cudaMalloc(&e->tf, 1024 * sizeof(cplx)));
+    CKC(cudaMalloc(&e->ti, 1024 * sizeof(cplx)));
+    {
+        std::vector<cplx> tf(1024), ti(1024);
+        make_twiddles(tf.data(), ti.data());
+        CKC(cudaMemcpy(e->tf, tf.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    CKC(cudaMalloc(&e->luts, (size_t)e->cap_luts * kN * sizeof(u64)));
+    CKC(cudaMalloc(&e->bsk_f, (size_t)p->n * kBskStepElems * sizeof(cplx)));
+    CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
+    CKC(cudaMalloc(&e->ksk_corr, (size_t)(p->n + 1) * sizeof(u64)));
+    CKC(blind_rotate_configure());
+    CKC(cudaStreamSynchronize(e->stream));
+#undef CKC
+    *out = e;
+    return FHESTR_OK;
+}
+
+void fhestr_engine_destroy(fhestr_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    if (e->own_arena && e->arena) cudaFree(e->arena);
+    cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
+    cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int fhestr_set_stream(fhestr_engine* e, void* cuda_stream) {
+    if (!e) return FHESTR_E_INVALID;
+    e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    return FHESTR_OK;
+}
+
+int fhestr_sync(fhestr_engine* e) {
+    if (!e) return FHESTR_E_INVALID;
+    CK(cudaStreamSynchronize(e->stream));
+    return FHESTR_OK;
+}
+
+void* fhestr_arena_ptr(fhestr_engine* e) { return e ? e->arena : nullptr; }
+
+int fhestr_load_keys(fhestr_engine* e, const uint64_t* bsk_std, const uint64_t* ksk) {
+    if (!e || !bsk_std || !ksk) return e ? fail(e, FHESTR_E_INVALID, "null key pointer") : FHESTR_E_INVALID;
+    CK(cudaSetDevice(e->device));
+    const fhestr_params& p = e->prm;
+    const size_t bsk_words = (size_t)p.n * 4 * kN;
+    const size_t ksk_words = (size_t)kN * p.ks_level * (p.n + 1);
+    u64* d_std = nullptr;
+    CK(cudaMalloc(&d_std, bsk_words * sizeof(u64)));
+    CK(cudaMemcpyAsync(d_std, bsk_std, bsk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->ksk, ksk, ksk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
+    e->launches += launch_bsk_convert(d_std, p.n, e->tf, e->bsk_f, e->stream);
+    e->launches += launch_ksk_correction(e->ksk, kN * p.ks_level, p.n, p.ks_base_log, e->ksk_corr, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaFree(d_std));
+    e->keys_loaded = true;
+    return FHESTR_OK;
+}
+
+static int stage_bytes(fhestr_engine* e, const uint8_t* host, size_t n) {
+    if (n > e->bytes_cap) {
+        if (e->d_bytes) CK(cudaFree(e->d_bytes));
+        e->bytes_cap = n * 2 + 256;
+        CK(cudaMalloc(&e->d_bytes, e->bytes_cap));
+    }
+    CK(cudaMemcpyAsync(e->d_bytes, host, n, cudaMemcpyHostToDevice, e->stream));
+    return FHESTR_OK;
+}
+
+int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id) {
+    if (!e || !table || !lut_id) return FHESTR_E_INVALID;
+    if (e->n_luts >= e->cap_luts) return fail(e, FHESTR_E_STATE, "LUT registry full");
+    CK(cudaSetDevice(e->device));
+    const int entries = 1 << (63 - e->prm.delta_log);
+    int rc = stage_bytes(e, table, entries);
+    if (rc) return rc;
+    e->launches += launch_lut_poly(e->d_bytes, entries, e->prm.delta_log, e->luts + (size_t)e->n_luts * kN, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));  // d_bytes is reused by the next call
+    *lut_id = e->n_luts++;
+    return FHESTR_OK;
+}
+
+int fhestr_lut_download(fhestr_engine* e, int32_t lut_id, uint64_t* out_poly) {
+    if (!e || !out_poly || lut_id < 0 || lut_id >= e->n_luts) return e ? fail(e, FHESTR_E_INVALID, "bad lut id") : FHESTR_E_INVALID;
+    CK(cudaMemcpyAsync(out_poly, e->luts + (size_t)lut_id * kN, kN * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FHESTR_OK;
+}
+
+int fhestr_ct_upload(fhestr_engine* e, uint32_t first, uint32_t count, const uint64_t* host) {
+    if (!e || !host) return FHESTR_E_INVALID;
+    if ((uint64_t)first + count > e->arena_blocks) return fail(e, FHESTR_E_STATE, "upload outside the arena");
+    CK(cudaMemcpyAsync(e->arena + (size_t)first * (kN + 1), host, (size_t)count * (kN + 1) * sizeof(u64),
+                       cudaMemcpyHostToDevice, e->stream));
+    return FHESTR_OK;
+}
+
+int fhestr_ct_download(fhestr_engine* e, uint32_t first, uint32_t count, uint64_t* host) {
+    if (!e || !host) return FHESTR_E_INVALID;
+    if ((uint64_t)first + count > e->arena_blocks) return fail(e, FHESTR_E_STATE, "download outside the arena");
+    CK(cudaMemcpyAsync(host, e->arena + (size_t)first * (kN + 1), (size_t)count * (kN + 1) * sizeof(u64),
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FHESTR_OK;
+}
+
+int fhestr_ct_trivial(fhestr_engine* e, uint32_t first, uint32_t count, const uint8_t* values) {
+    if (!e || !values) return FHESTR_E_INVALID;
+    if ((uint64_t)first + count > e->arena_blocks) return fail(e, FHESTR_E_STATE, "trivial outside the arena");
+    int rc = stage_bytes(e, values, count);
+    if (rc) return rc;
+    e->launches += launch_trivial(e->arena, first, count, e->d_bytes, e->prm.delta_log, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return FHESTR_OK;
+}
+
+// launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
+static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all) {
+    if (n_pbs) {
+        KsBatchArgs ks{d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_pbs,
+                       e->prm.ks_base_log, e->prm.ks_level};
+        e->launches += launch_keyswitch(ks, e->stream);
+        BrBatchArgs br{};
+        br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
+        br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
+        e->launches += launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+    }
+    if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
+    CK(cudaGetLastError());
+    return FHESTR_OK;
+}
+
+// stable partition: PBS jobs first, leveled jobs after; returns the number of PBS jobs
+static uint32_t partition_jobs(const fhestr_job* in, uint32_t n, fhestr_job* out) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) if (in[i].lut >= 0) out[k++] = in[i];
+    const uint32_t n_pbs = k;
+    for (uint32_t i = 0; i < n; i++) if (in[i].lut < 0) out[k++] = in[i];
+    return n_pbs;
+}
+
+int fhestr_pbs_batch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_jobs) {
+    if (!e || (!jobs && n_jobs)) return FHESTR_E_INVALID;
+    if (!e->keys_loaded) return fail(e, FHESTR_E_STATE, "keys not loaded");
+    if (!n_jobs) return FHESTR_OK;
+    int rc = validate_jobs(e, jobs, n_jobs);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    rc = ensure_scratch(e, n_jobs);
+    if (rc) return rc;
+    std::vector<fhestr_job> sorted(n_jobs);
+    const uint32_t n_pbs = partition_jobs(jobs, n_jobs, sorted.data());
+    CK(cudaMemcpyAsync(e->d_jobs, sorted.data(), (size_t)n_jobs * sizeof(fhestr_job), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // `sorted` is pageable host memory
+    return run_level(e, e->d_jobs, n_pbs, n_jobs);
+}
+
+int fhestr_program_create(fhestr_engine* e, const fhestr_job* jobs, const uint32_t* level_offsets,
+                          uint32_t n_levels, fhestr_program** out) {
+    if (!e || !jobs || !level_offsets || !out) return FHESTR_E_INVALID;
+    const uint32_t total = level_offsets[n_levels];
+    int rc = validate_jobs(e, jobs, total);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    fhestr_program* p = new (std::nothrow) fhestr_program();
+    if (!p) return fail(e, FHESTR_E_STATE, "out of host memory");
+    p->eng = e;
+    p->level_off.assign(level_offsets, level_offsets + n_levels + 1);
+    p->level_pbs.resize(n_levels);
+    std::vector<fhestr_job> sorted(total ? total : 1);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t a = level_offsets[l], b = level_offsets[l + 1];
+        p->level_pbs[l] = partition_jobs(jobs + a, b - a, sorted.data() + a);
+        if (p->level_pbs[l] > p->max_level_pbs) p->max_level_pbs = p->level_pbs[l];
+    }
+    cudaError_t ce = cudaMalloc(&p->d_jobs, (size_t)(total ? total : 1) * sizeof(fhestr_job));
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy(p->d_jobs, sorted.data(), (size_t)total * sizeof(fhestr_job), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        cudaFree(p->d_jobs);
+        delete p;
+        return fail(e, FHESTR_E_CUDA, std::string("program upload: ") + cudaGetErrorString(ce));
+    }
+    *out = p;
+    return FHESTR_OK;
+}
+
+int fhestr_program_level_jobs(const fhestr_program* p, uint32_t level, uint32_t* n_jobs) {
+    if (!p || !n_jobs || level + 1 >= p->level_off.size()) return FHESTR_E_INVALID;
+    *n_jobs = p->level_off[level + 1] - p->level_off[level];
+    return FHESTR_OK;
+}
+
+int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level, uint32_t last_level,
+                       uint32_t rank, uint32_t world) {
+    if (!e || !p || p->eng != e || world == 0 || rank >= world) return FHESTR_E_INVALID;
+    if (!e->keys_loaded) return fail(e, FHESTR_E_STATE, "keys not loaded");
+    if (last_level > p->level_pbs.size() || first_level > last_level) return fail(e, FHESTR_E_INVALID, "bad level range");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_scratch(e, p->max_level_pbs);
+    if (rc) return rc;
+    for (uint32_t l = first_level; l < last_level; l++) {
+        const uint32_t a = p->level_off[l], n_all = p->level_off[l + 1] - a, n_pbs = p->level_pbs[l];
+        // shard the PBS jobs of the level across ranks (contiguous slices); leveled jobs are cheap and
+        // replicated on every rank so that no exchange is needed for them
+        const uint32_t per = (n_pbs + world - 1) / world;
+        const uint32_t lo = per * rank < n_pbs ? per * rank : n_pbs;
+        const uint32_t hi = lo + per < n_pbs ? lo + per : n_pbs;
+        if (world == 1) {
+            rc = run_level(e, p->d_jobs + a, n_pbs, n_all);
+        } else {
+            rc = run_level(e, p->d_jobs + a + lo, hi - lo, hi - lo);
+            if (!rc && n_all > n_pbs) {
+                e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
+                CK(cudaGetLastError());
+            }
+        }
+        if (rc) return rc;
+    }
+    return FHESTR_OK;
+}
+
+void fhestr_program_destroy(fhestr_program* p) {
+    if (!p) return;
+    cudaFree(p->d_jobs);
+    delete p;
+}
+
+int fhestr_debug_keyswitch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_jobs, uint64_t* host_out) {
+    if (!e || !jobs || !host_out) return FHESTR_E_INVALID;
+    if (!e->keys_loaded) return fail(e, FHESTR_E_STATE, "keys not loaded");
+    int rc = validate_jobs(e, jobs, n_jobs);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->device));
+    rc = ensure_scratch(e, n_jobs);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->d_jobs, jobs, (size_t)n_jobs * sizeof(fhestr_job), cudaMemcpyHostToDevice, e->stream));
+    KsBatchArgs ks{e->d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_jobs,
+                   e->prm.ks_base_log, e->prm.ks_level};
+    e->launches += launch_keyswitch(ks, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_out, e->ks_out, (size_t)n_jobs * (e->prm.n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return FHESTR_OK;
+}
+
+int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const int32_t* lut_ids,
+                              const uint64_t* init_acc_host, uint32_t count, uint64_t* acc_out_host) {
+    if (!e || !ks_host || !acc_out_host || (!lut_ids && !init_acc_host)) return FHESTR_E_INVALID;
+    if (!e->keys_loaded) return fail(e, FHESTR_E_STATE, "keys not loaded");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_scratch(e, count);
+    if (rc) return rc;
+    const size_t acc_bytes = (size_t)count * 2 * kN * sizeof(u64);
+    u64 *d_init = nullptr, *d_out = nullptr;
+    int32_t* d_ids = nullptr;
+    CK(cudaMalloc(&d_out, acc_bytes));
+    CK(cudaMalloc(&d_ids, count * sizeof(int32_t)));
+    std::vector<int32_t> ids(count, 0);
+    if (lut_ids) ids.assign(lut_ids, lut_ids + count);
+    for (auto v : ids) if (v < 0 || (v >= e->n_luts && !init_acc_host)) { cudaFree(d_out); cudaFree(d_ids); return fail(e, FHESTR_E_INVALID, "bad lut id"); }
+    CK(cudaMemcpyAsync(d_ids, ids.data(), count * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (init_acc_host) {
+        CK(cudaMalloc(&d_init, acc_bytes));
+        CK(cudaMemcpyAsync(d_init, init_acc_host, acc_bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    CK(cudaMemcpyAsync(e->ks_out, ks_host, (size_t)count * (e->prm.n + 1) * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
+    BrBatchArgs br{};
+    br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = d_ids; br.jobs = nullptr; br.arena = e->arena;
+    br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.init_acc = d_init; br.out_acc = d_out;
+    br.n = e->prm.n; br.B = (int)count;
+    e->launches += launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(acc_out_host, d_out, acc_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_init); cudaFree(d_out); cudaFree(d_ids);
+    return FHESTR_OK;
+}
+
+int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_mhz_hint) {
+    if (!e || !tflops) return FHESTR_E_INVALID;
+    CK(cudaSetDevice(e->device));
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, 148 * 8 * 256 * sizeof(double)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    unsigned long long fmas = 0;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(a, e->stream));
+        e->launches += launch_dfma_peak(sink, 4096, &fmas, e->stream);
+        CK(cudaEventRecord(b, e->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double tf = 2.0 * (double)fmas / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    if (sm_clock_mhz_hint) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
+        *sm_clock_mhz_hint = khz / 1000.0;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    return FHESTR_OK;
+}
+
+uint64_t fhestr_kernel_launches(const fhestr_engine* e) { return e ? e->launches : 0; }
+
+int fhestr_set_pbs_per_cta(fhestr_engine* e, int v) {
+    if (!e || (v != 0 && v != 1 && v != 2 && v != 4)) return FHESTR_E_INVALID;
+    e->pbs_per_cta = v;
+    return FHESTR_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

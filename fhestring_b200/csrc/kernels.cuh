@@ -1,0 +1,51 @@
+// kernels.cuh -- launcher declarations shared by engine.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fhestr_engine.h"
+#include "br_core.cuh"
+
+namespace fhestr {
+
+struct BrBatchArgs {
+    const u64* ks;            // [B][n+1] keyswitched LWEs
+    const u64* luts;          // [n_luts][N] body polynomials
+    const int32_t* lut_ids;   // [B] (one per job; taken from jobs when jobs != nullptr)
+    const fhestr_job* jobs;   // [B] device job list (dst + lut) or nullptr
+    u64* arena;               // [blocks][N+1]
+    const cplx* bsk;          // Fourier BSK, engine layout
+    const cplx* tf;
+    const cplx* ti;
+    const u64* init_acc;      // optional [B][2][N]
+    u64* out_acc;             // optional [B][2][N]
+    int n;
+    int B;
+};
+
+struct KsBatchArgs {
+    const fhestr_job* jobs;   // [B] device
+    const u64* arena;         // [blocks][N+1]
+    const u64* ksk;           // [N][L][n+1]
+    const u64* ksk_corr;      // [n+1]  2^(base_log-1) * sum_{i,lvl} ksk[i][lvl][c]
+    u64* ks_out;              // [B][n+1]
+    int n, B, base_log, level;
+};
+
+// K0+K1: linear combination + LWE keyswitch.  Returns the number of kernels launched.
+int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s);
+// K2+K3+K4: mod-switch + blind rotation + sample extract.  pbs_per_cta in {0 (auto), 1, 2, 4}.
+int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s);
+cudaError_t blind_rotate_configure();  // opt in to the large dynamic shared memory carve-out
+// leveled jobs (lut < 0): dst = sum coeff*src + constant*e_body
+int launch_linear(const fhestr_job* jobs, int B, u64* arena, cudaStream_t s);
+// K5: 16-entry table -> body polynomial
+int launch_lut_poly(const uint8_t* table_dev, int entries, int delta_log, u64* out, cudaStream_t s);
+// K6: standard-domain BSK [n][2][2][N] -> Fourier layout [n][kBskStepElems]
+int launch_bsk_convert(const u64* bsk_std, int n, const cplx* tf, cplx* out, cudaStream_t s);
+int launch_ksk_correction(const u64* ksk, int rows /* N*L */, int n, int base_log, u64* corr, cudaStream_t s);
+int launch_trivial(u64* arena, uint32_t first, uint32_t count, const uint8_t* values_dev, int delta_log, cudaStream_t s);
+// DFMA microbenchmark; returns total FMA count issued through *fmas
+int launch_dfma_peak(double* sink, int iters, unsigned long long* fmas, cudaStream_t s);
+
+}  // namespace fhestr
