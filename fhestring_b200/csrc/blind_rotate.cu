@@ -79,7 +79,7 @@ cudaError_t blind_rotate_configure() {
 int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s) {
     if (a.B <= 0) return 0;
     int P = pbs_per_cta;
-    if (P != 1 && P != 2 && P != 4) P = (a.B >= 4 * 148) ? 4 : (a.B >= 2 * 148 ? 2 : 1);
+    if (P != 1 && P != 2 && P != 4) P = 1;  // measured: independent 64-thread CTAs drift out of phase and overlap FP64 with shared-memory phases; P=4 runs in lockstep and is 1.47x slower
     const int grid = (a.B + P - 1) / P;
     switch (P) {
         case 1: blind_rotate_kernel<1><<<grid, 64, 1 * kPairSmemBytes, s>>>(a); break;

@@ -148,6 +148,7 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
     CKC(cudaMalloc(&e->ksk_corr, (size_t)(p->n + 1) * sizeof(u64)));
     CKC(blind_rotate_configure());
+    CKC(keyswitch_configure());
     CKC(cudaStreamSynchronize(e->stream));
 #undef CKC
     *out = e;

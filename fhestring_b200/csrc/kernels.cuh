@@ -36,7 +36,8 @@ struct KsBatchArgs {
 int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s);
 // K2+K3+K4: mod-switch + blind rotation + sample extract.  pbs_per_cta in {0 (auto), 1, 2, 4}.
 int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s);
-cudaError_t blind_rotate_configure();  // opt in to the large dynamic shared memory carve-out
+cudaError_t blind_rotate_configure();
+cudaError_t keyswitch_configure();  // opt in to the large dynamic shared memory carve-out
 // leveled jobs (lut < 0): dst = sum coeff*src + constant*e_body
 int launch_linear(const fhestr_job* jobs, int B, u64* arena, cudaStream_t s);
 // K5: 16-entry table -> body polynomial

@@ -133,10 +133,18 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
     }
 }
 
+constexpr size_t kKsSmemBytes = (size_t)kN * kKsBT * 4 + kKsBT * 8;
+
+cudaError_t keyswitch_configure() {
+    cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(keyswitch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes);
+}
+
 int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s) {
     if (a.B <= 0) return 0;
     const int grid = (a.B + kKsBT - 1) / kKsBT;
-    const size_t smem = (size_t)kN * kKsBT * 4 + kKsBT * 8;
+    const size_t smem = kKsSmemBytes;
     if (a.level == 5) keyswitch_kernel<5><<<grid, kKsThreads, smem, s>>>(a);
     else keyswitch_kernel<0><<<grid, kKsThreads, smem, s>>>(a);
     return 1;

@@ -74,7 +74,9 @@ def full_checks(B=4096):
     o = Oracle(**PO)
     t = time.time(); keys = o.keygen(1); print("keygen", round(time.time() - t, 2), "s")
     eng = Engine(arena_blocks=2 * B + 16, **PE)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
     t = time.time(); eng.load_keys(keys.bsk, keys.ksk); print("load_keys", round(time.time() - t, 2), "s")
     rng = np.random.default_rng(2)
     vals = rng.integers(0, 16, B)
@@ -106,5 +108,5 @@ def full_checks(B=4096):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    small_checks()
+    if "--skip-small" not in sys.argv: small_checks()
     full_checks(int(sys.argv[1]) if len(sys.argv) > 1 else 4096)

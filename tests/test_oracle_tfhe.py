@@ -1,0 +1,136 @@
+"""CPU tests of the TFHE oracle itself (oracle/tfhe_oracle.c): the conventions of SURVEY.md Appendix A
+are checked against their defining properties, and the scheme-level behaviour (decrypt(PBS(x)) == f(x),
+noise inside the analytic budget) is checked at the real parameter set.  Ciphertext-level parity with
+tfhe-rs is unpinned (no golden vectors exist in the reference)."""
+import numpy as np
+import pytest
+
+from oracle.tfhe_oracle import Oracle, PARAM_MESSAGE_2_CARRY_2_KS_PBS as P
+
+
+def test_decomposer_closest_representable_and_balanced(small_oracle):
+    o, _ = small_oracle
+    rng = np.random.default_rng(0)
+    xs = [0, 1, 2**63, 2**64 - 1, 2**40, 2**40 - 1, 2**41 + 2**40, (2**22) << 41] + [int(v) for v in rng.integers(0, 2**64, 500, dtype=np.uint64)]
+    for base_log, level in [(23, 1), (3, 5), (4, 3), (2, 8)]:
+        rep = base_log * level
+        for x in xs:
+            d = o.decompose(x, base_log, level)
+            assert np.all(d >= -(1 << (base_log - 1))) and np.all(d <= (1 << (base_log - 1)))
+            recomposed = sum(int(d[l]) << (64 - base_log * (l + 1)) for l in range(level)) % 2**64
+            closest = (((x >> (64 - rep - 1)) + 1) >> 1) << (64 - rep)
+            assert recomposed == closest % 2**64, (x, base_log, level)
+            err = (x - recomposed + 2**63) % 2**64 - 2**63
+            assert abs(err) <= 1 << (64 - rep - 1)
+
+
+def test_decomposer_tie_goes_up(small_oracle):
+    o, _ = small_oracle
+    # state == B/2 exactly with nothing above: digit +B/2, not -B/2 (A.4)
+    assert o.decompose((1 << 22) << 41, 23, 1)[0] == 1 << 22
+    assert o.decompose(((1 << 22) + 1) << 41, 23, 1)[0] == (1 << 22) + 1 - (1 << 23)
+
+
+def test_modswitch_range_and_rounding(small_oracle):
+    o, _ = small_oracle
+    assert o.modswitch(0) == 0
+    assert o.modswitch(2**64 - 1) == 4096  # may equal 2N, which is the identity rotation
+    assert o.modswitch(1 << 52) == 1
+    assert o.modswitch((1 << 51)) == 1      # rounds half up
+    assert o.modswitch((1 << 51) - 1) == 0
+
+
+def test_lut_poly_layout(small_oracle):
+    o, _ = small_oracle
+    table = [(5 * x + 3) % 16 for x in range(16)]
+    lut = o.lut_poly(table)
+    box = 2048 // 16
+    for m in range(16):
+        centre = m * box
+        assert lut[centre] == np.uint64(table[m] << 59)
+        if m:
+            assert lut[centre - box // 2] == np.uint64(table[m] << 59)
+    # the wrapped half box of entry 0 carries the negacyclic sign
+    assert lut[2047] == np.uint64((-(table[0] << 59)) % 2**64)
+
+
+def test_keyswitch_preserves_phase(small_oracle):
+    o, keys = small_oracle
+    vals = np.arange(16)
+    cts = o.encrypt_big(keys, vals, seed=3)
+    ks = o.keyswitch(keys, cts)
+    ph = o.phases(keys.s_lwe, ks)
+    assert np.array_equal(o.decode(ph), vals)
+    err = (ph.astype(np.int64) - (vals.astype(np.int64) << 59)).astype(float) / 2.0**64
+    assert np.abs(err).max() < 2e-2  # KS noise (std ~1.7e-3 at these parameters) is far from 1/32
+
+
+@pytest.mark.parametrize("table", [list(range(16)), [(x * x) % 16 for x in range(16)],
+                                   [int((x >> 2) == (x & 3)) for x in range(16)]])
+def test_pbs_exact_and_fft_decrypt(small_oracle, table):
+    o, keys = small_oracle
+    vals = np.arange(16)
+    cts = o.encrypt_big(keys, vals, seed=4)
+    lut = o.lut_poly(table)
+    out = o.pbs_exact(keys, lut[None], [0] * 16, cts)
+    assert np.array_equal(o.decrypt_big(keys, out), np.array(table))
+    out2, _ = o.pbs_fft(keys, o.fourier_bsk(keys), lut[None], [0] * 16, cts)
+    assert np.array_equal(o.decrypt_big(keys, out2), np.array(table))
+
+
+def test_padding_bit_gives_negated_lut(small_oracle):
+    """the compare recipe relies on it: input value v+16 yields -f(v)"""
+    o, keys = small_oracle
+    table = [(3 * x + 1) % 16 for x in range(16)]
+    cts = o.encrypt_big(keys, 16 + np.arange(16), seed=5)
+    out = o.pbs_exact(keys, o.lut_poly(table)[None], [0] * 16, cts)
+    assert np.array_equal(o.decrypt_big(keys, out), (-np.array(table)) % 16)
+
+
+def test_trivial_input_pbs(small_oracle):
+    o, keys = small_oracle
+    table = [(7 * x + 2) % 16 for x in range(16)]
+    cts = np.zeros((16, o.big), np.uint64)
+    cts[:, -1] = np.arange(16, dtype=np.uint64) << np.uint64(59)
+    out = o.pbs_exact(keys, o.lut_poly(table)[None], [0] * 16, cts)
+    assert np.array_equal(o.decrypt_big(keys, out), np.array(table))
+
+
+def test_sample_extract_matches_glwe_phase(small_oracle):
+    o, keys = small_oracle
+    rng = np.random.default_rng(6)
+    acc = rng.integers(0, 2**64, (2, 2048), dtype=np.uint64)
+    lwe = o.sample_extract(acc)
+    # phase of GLWE at coefficient 0: B_0 - sum_j A_j * S_{(0-j) mod N} with negacyclic sign
+    s = keys.s_glwe.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        a_s0 = acc[0][0] * s[0] - np.sum(acc[0][1:] * s[::-1][:-1])
+        want = acc[1][0] - a_s0
+    assert o.phases(keys.s_glwe, lwe[None])[0] == want
+
+
+def test_full_parameter_pbs_noise_budget(full_oracle):
+    """real parameter set: all 16 values decode correctly through the f64-FFT route and the output
+    noise matches the analytic budget of SURVEY.md 8d (std ~ 2^-15.5 of the torus)."""
+    o, keys = full_oracle
+    vals = np.arange(32) % 16
+    cts = o.encrypt_big(keys, vals, seed=7)
+    lut = o.lut_poly(list(range(16)))
+    out, _ = o.pbs_fft(keys, o.fourier_bsk(keys), lut[None], [0] * 32, cts)
+    assert np.array_equal(o.decrypt_big(keys, out), vals)
+    err = (o.phases(keys.s_glwe, out).astype(np.int64) - (vals.astype(np.int64) << 59)).astype(float) / 2.0**64
+    var_analytic = 4.5e-10
+    assert np.var(err) < 2.0 * var_analytic
+    assert np.abs(err).max() < 1.0 / 64
+
+
+def test_fft_external_product_close_to_exact(small_oracle):
+    """calibration of the blind-rotation tolerance: the CPU f64 route against exact integers"""
+    o, keys = small_oracle
+    rng = np.random.default_rng(8)
+    glwe = rng.integers(0, 2**64, (2, 2048), dtype=np.uint64)
+    acc = rng.integers(0, 2**64, (2, 2048), dtype=np.uint64)
+    want = o.external_product_exact(keys.bsk[0], glwe, acc)
+    got = o.external_product_fft(o.fourier_bsk(keys)[: 4 * 2048], glwe, acc)
+    d = (got - want).astype(np.int64).astype(float)
+    assert np.sqrt(np.mean(d * d)) < 2.0**40  # 2^-24 of the torus
