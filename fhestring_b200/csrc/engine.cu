@@ -40,6 +40,9 @@ struct fhestr_engine {
     size_t bytes_cap = 0;
     int pbs_per_cta = 0;
     uint64_t launches = 0;
+    bool timing = false;
+    struct Timed { cudaEvent_t a, b, c; uint32_t pbs; };   // a..b keyswitch, b..c blind rotation
+    std::vector<Timed> timed;
     std::string err;
 };
 
@@ -261,13 +264,21 @@ int fhestr_ct_trivial(fhestr_engine* e, uint32_t first, uint32_t count, const ui
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
 static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all) {
     if (n_pbs) {
+        fhestr_engine::Timed t{};
+        if (e->timing) {
+            CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); CK(cudaEventCreate(&t.c));
+            t.pbs = n_pbs;
+            CK(cudaEventRecord(t.a, e->stream));
+        }
         KsBatchArgs ks{d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_pbs,
                        e->prm.ks_base_log, e->prm.ks_level};
         e->launches += launch_keyswitch(ks, e->stream);
+        if (e->timing) CK(cudaEventRecord(t.b, e->stream));
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
         br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
         e->launches += launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+        if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
     CK(cudaGetLastError());
@@ -452,6 +463,38 @@ int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_
 }
 
 uint64_t fhestr_kernel_launches(const fhestr_engine* e) { return e ? e->launches : 0; }
+
+static void drop_timed(fhestr_engine* e) {
+    for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); cudaEventDestroy(t.c); }
+    e->timed.clear();
+}
+
+int fhestr_set_timing(fhestr_engine* e, int enable) {
+    if (!e) return FHESTR_E_INVALID;
+    CK(cudaStreamSynchronize(e->stream));
+    drop_timed(e);
+    e->timing = enable != 0;
+    return FHESTR_OK;
+}
+
+int fhestr_get_timing(fhestr_engine* e, double* ks_ms, double* br_ms, uint64_t* br_launches, uint64_t* br_pbs) {
+    if (!e) return FHESTR_E_INVALID;
+    CK(cudaStreamSynchronize(e->stream));
+    double ks = 0, br = 0;
+    uint64_t pbs = 0;
+    for (auto& t : e->timed) {
+        float m1 = 0, m2 = 0;
+        CK(cudaEventElapsedTime(&m1, t.a, t.b));
+        CK(cudaEventElapsedTime(&m2, t.b, t.c));
+        ks += m1; br += m2; pbs += t.pbs;
+    }
+    if (ks_ms) *ks_ms = ks;
+    if (br_ms) *br_ms = br;
+    if (br_launches) *br_launches = e->timed.size();
+    if (br_pbs) *br_pbs = pbs;
+    drop_timed(e);
+    return FHESTR_OK;
+}
 
 int fhestr_set_pbs_per_cta(fhestr_engine* e, int v) {
     if (!e || (v != 0 && v != 1 && v != 2 && v != 4)) return FHESTR_E_INVALID;

@@ -148,6 +148,16 @@ class Engine:
     def set_pbs_per_cta(self, v: int):
         self._ck(self.lib.fhestr_set_pbs_per_cta(self.h, C.c_int(v)))
 
+    def set_timing(self, enable: bool):
+        self._ck(self.lib.fhestr_set_timing(self.h, C.c_int(1 if enable else 0)))
+
+    def get_timing(self):
+        """(keyswitch_ms, blind_rotate_ms, blind_rotate_launches, blind_rotate_pbs) since the last call"""
+        ks, br = C.c_double(), C.c_double()
+        nl, npbs = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.fhestr_get_timing(self.h, C.byref(ks), C.byref(br), C.byref(nl), C.byref(npbs)))
+        return ks.value, br.value, int(nl.value), int(npbs.value)
+
     # -- keys / LUTs
     def load_keys(self, bsk_std: np.ndarray, ksk: np.ndarray):
         bsk_std = np.ascontiguousarray(bsk_std, np.uint64)
@@ -237,3 +247,4 @@ def single_term_jobs(dst, src, lut) -> np.ndarray:
     jobs["src"][:, 0] = src
     jobs["coeff"][:, 0] = 1
     return jobs
+

@@ -38,7 +38,7 @@ extern "C" {
 typedef struct fhestr_engine fhestr_engine;
 
 /* TFHE parameter set, passed as data and validated.  Supported by the kernels:
- * N = 2048, k = 1, pbs_level = 1, pbs_base_log = 23, n <= 1023, (ks_base_log+1)*ks_level <= 32. */
+ * N = 2048, k = 1, pbs_level = 1, pbs_base_log = 23, n <= 767, (ks_base_log+1)*ks_level <= 32. */
 typedef struct {
     int32_t n;            /* small LWE dimension (742) */
     int32_t N;            /* polynomial size (2048) */
@@ -121,6 +121,32 @@ int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
 /* blind-rotation launch shape override for experiments: PBS per CTA (1, 2 or 4; 0 = automatic) */
 int fhestr_set_pbs_per_cta(fhestr_engine* e, int pbs_per_cta);
+
+/* per-kernel device timing (CUDA events on the engine stream around every keyswitch / blind-rotation
+ * launch); get_timing synchronises the stream and returns the totals since the last reset */
+int fhestr_set_timing(fhestr_engine* e, int enable);
+int fhestr_get_timing(fhestr_engine* e, double* keyswitch_ms, double* blind_rotate_ms,
+                      uint64_t* blind_rotate_launches, uint64_t* blind_rotate_pbs);
+
+/* ---- client side (replaces MyClientKey, /root/reference/src/client_key.rs:9-106): host-only ------- */
+/* Key generation, block/string encryption and decryption.  Runs on the CPU like the reference's
+ * client; it is not on the PBS path.  Deterministic for a given seed. */
+typedef struct fhestr_client fhestr_client;
+int fhestr_client_create(const fhestr_params* params, double lwe_std, double glwe_std, uint64_t seed,
+                         fhestr_client** out);
+void fhestr_client_destroy(fhestr_client* c);
+/* gen_keys_radix (client_key.rs:31): fills the server key material in the layouts fhestr_load_keys takes */
+int fhestr_client_server_keys(fhestr_client* c, uint64_t* bsk_std, uint64_t* ksk);
+/* secret key bits, one byte per bit (tests use them to decrypt with the oracle) */
+int fhestr_client_secret_keys(const fhestr_client* c, uint8_t* s_lwe /* [n] */, uint8_t* s_glwe /* [N] */);
+/* block-level: values are raw block values (< 2^(64-delta_log)); ciphertexts are [count][N+1] u64 */
+int fhestr_client_encrypt_blocks(fhestr_client* c, const uint8_t* values, uint32_t count, uint64_t* cts);
+int fhestr_client_decrypt_blocks(const fhestr_client* c, const uint64_t* cts, uint32_t count,
+                                 uint8_t* values /* (phase + delta/2) >> delta_log, padding bit dropped */,
+                                 int64_t* phase_err /* optional: phase - value*delta, signed */);
+/* radix level (client_key.rs:45-106): one u8 = 4 blocks of 2 message bits, little endian */
+int fhestr_client_encrypt_u8(fhestr_client* c, const uint8_t* bytes, uint32_t count, uint64_t* cts /* [count][4][N+1] */);
+int fhestr_client_decrypt_u8(const fhestr_client* c, const uint64_t* cts, uint32_t count, uint8_t* bytes);
 
 #ifdef __cplusplus
 }
