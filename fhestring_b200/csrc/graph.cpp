@@ -1,0 +1,573 @@
+// graph.cpp -- see graph.h.  Recipes follow SURVEY.md 2.4/2.5 (tfhe-rs 0.5 radix ops over 2_2 blocks) in
+// VALUE: every op returns a clean char (blocks in [0,3]; flags: block 0 in {0,1}, blocks 1..3 trivial 0)
+// holding exactly the u8 the reference's op holds.  Where the reference's recipe does work that cannot
+// change the plaintext (PBS on trivial blocks, message_extract of an already clean sum, the full 8-PBS
+// subtract behind flip) the value-set analysis folds it away.
+#include "graph.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace fhestr {
+
+static inline int mod32(int v) { return ((v % 32) + 32) % 32; }
+static inline int popcount32(uint32_t v) { return __builtin_popcount(v); }
+
+int Graph::lut_id(const std::array<uint8_t, 16>& t) {
+    auto it = lut_ids.find(t);
+    if (it != lut_ids.end()) return it->second;
+    const int id = (int)lut_tables.size();
+    lut_tables.push_back(t);
+    lut_ids[t] = id;
+    return id;
+}
+
+BlockId Graph::trivial_block(int value) {
+    value = mod32(value);
+    if (!triv_cache_init) {
+        for (int v = 0; v < 32; v++) {
+            BlockNode n;
+            n.kind = BKind::Trivial;
+            n.vset = 1u << v;
+            n.cst = v;
+            triv_cache[v] = (BlockId)nodes.size();
+            nodes.push_back(n);
+        }
+        triv_cache_init = true;
+    }
+    return triv_cache[value];
+}
+
+int Graph::trivial_value(BlockId b) const { return nodes[b].cst; }
+
+BlockId Graph::input_block() {
+    BlockNode n;
+    n.kind = BKind::Input;
+    n.vset = 0xF;  // clean message block
+    n.noise2 = 1.f;
+    nodes.push_back(n);
+    return (BlockId)nodes.size() - 1;
+}
+
+uint32_t Graph::vset_of(const std::vector<std::pair<BlockId, int>>& ops, int cst) const {
+    uint32_t S = 1u << mod32(cst);
+    for (auto& op : ops) {
+        const uint32_t V = nodes[op.first].vset;
+        uint32_t T = 0;
+        for (int s = 0; s < 32; s++) {
+            if (!(S >> s & 1)) continue;
+            for (int v = 0; v < 32; v++) {
+                if (!(V >> v & 1)) continue;
+                const int sv = v >= 16 ? v - 32 : v;  // bit 4 set = negative value (padding bit)
+                T |= 1u << mod32(s + op.second * sv);
+            }
+        }
+        S = T;
+    }
+    return S;
+}
+
+void Graph::flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, std::vector<Term>& terms, int& out_cst) {
+    for (;;) {
+        std::map<BlockId, int> acc;
+        int c = cst;
+        BlockId widest = 0;
+        size_t widest_n = 0;
+        for (auto& op : ops) {
+            const BlockNode& n = nodes[op.first];
+            if (n.kind == BKind::Trivial) {
+                const int v = n.cst >= 16 ? n.cst - 32 : n.cst;
+                c += op.second * v;
+            } else if (n.kind == BKind::Linear && !n.materialized) {
+                for (auto& t : n.terms) acc[t.blk] += op.second * t.coeff;
+                c += op.second * n.cst;
+                if (n.terms.size() > widest_n) { widest_n = n.terms.size(); widest = op.first; }
+            } else {
+                acc[op.first] += op.second;
+            }
+        }
+        terms.clear();
+        for (auto& kv : acc) if (kv.second != 0) terms.push_back(Term{kv.first, kv.second});
+        out_cst = mod32(c);
+        if (terms.size() <= FHESTR_MAX_TERMS) return;
+        if (widest_n <= 1) { fail("linear combination needs more than FHESTR_MAX_TERMS atoms"); terms.resize(FHESTR_MAX_TERMS); return; }
+        nodes[widest].materialized = true;  // becomes an atom with its own leveled job
+    }
+}
+
+float Graph::noise2_of(const std::vector<Term>& terms) const {
+    float s = 0;
+    for (auto& t : terms) s += (float)t.coeff * (float)t.coeff * nodes[t.blk].noise2;
+    return s;
+}
+
+// a materialised Linear atom is written by the leveled section of its level, so a Linear consumer
+// (same section) has to wait one level; PBS consumers are one level later anyway
+int Graph::level_of(const std::vector<Term>& terms, bool for_linear) const {
+    int l = 0;
+    for (auto& t : terms) {
+        const BlockNode& n = nodes[t.blk];
+        l = std::max(l, (int)n.level + ((for_linear && n.kind == BKind::Linear) ? 1 : 0));
+    }
+    return l;
+}
+
+BlockId Graph::lin(const std::vector<std::pair<BlockId, int>>& ops, int cst, uint32_t declared_vset) {
+    std::vector<Term> terms;
+    int c;
+    flatten(ops, cst, terms, c);
+    if (terms.empty()) return trivial_block(c);
+    if (terms.size() == 1 && terms[0].coeff == 1 && c == 0) return terms[0].blk;
+    BlockNode n;
+    n.kind = BKind::Linear;
+    n.vset = declared_vset ? declared_vset : vset_of(ops, cst);
+    n.terms = terms;
+    n.cst = c;
+    n.noise2 = noise2_of(terms);
+    n.level = level_of(terms, true);
+    nodes.push_back(n);
+    return (BlockId)nodes.size() - 1;
+}
+
+static std::array<uint8_t, 16> table_of(const std::function<int(int)>& f) {
+    std::array<uint8_t, 16> t;
+    for (int v = 0; v < 16; v++) t[v] = (uint8_t)(f(v) & 15);
+    return t;
+}
+
+BlockId Graph::refresh(BlockId b) {
+    return pbs({{b, 1}}, 0, table_of([](int v) { return v; }));
+}
+
+// scope in which PBS inputs may carry the padding bit (negative values): the comparison recipe
+struct SignedScope {
+    bool& flag;
+    bool prev;
+    explicit SignedScope(bool& f) : flag(f), prev(f) { flag = true; }
+    ~SignedScope() { flag = prev; }
+};
+
+BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, const std::array<uint8_t, 16>& table) {
+    std::vector<std::pair<BlockId, int>> ops = ops_in;
+    const uint32_t S = vset_of(ops, cst);
+    if (S >> 16 & 1) fail("PBS input can reach the ambiguous value 16");
+    if (!signed_ok && (S >> 16)) fail("PBS input overflows into the padding bit");
+    // image of the value set; padding-bit inputs give -f(v-16)
+    uint32_t O = 0;
+    for (int v = 0; v < 32; v++) {
+        if (!(S >> v & 1)) continue;
+        O |= 1u << (v < 16 ? table[v] : mod32(-(int)table[v - 16]));
+    }
+    if (popcount32(O) == 1) return trivial_block(__builtin_ctz(O));
+
+    std::vector<Term> terms;
+    int c;
+    flatten(ops, cst, terms, c);
+    // keep the input inside the variance the reference's own recipes use (graph.h): refresh the
+    // noisiest lazily-summed operand until it fits
+    for (int guard = 0; noise2_of(terms) > kNoise2Limit && guard < 8; guard++) {
+        int worst = -1;
+        float worst_c = 0;
+        for (size_t i = 0; i < ops.size(); i++) {
+            const BlockNode& n = nodes[ops[i].first];
+            if (n.kind != BKind::Linear || n.noise2 <= 1.f || n.noise2 > kNoise2Limit || (n.vset >> 16)) continue;
+            const float contrib = (float)ops[i].second * ops[i].second * n.noise2;
+            if (contrib > worst_c) { worst_c = contrib; worst = (int)i; }
+        }
+        if (worst < 0) { fail("noise budget exceeded and nothing to refresh"); break; }
+        ops[worst].first = refresh(ops[worst].first);
+        flatten(ops, cst, terms, c);
+    }
+
+    const int lid = lut_id(table);
+    std::string key;
+    key.reserve(16 + terms.size() * 8);
+    key.append(reinterpret_cast<const char*>(&lid), 4);
+    key.append(reinterpret_cast<const char*>(&c), 4);
+    for (auto& t : terms) key.append(reinterpret_cast<const char*>(&t), sizeof(Term));
+    auto it = cse.find(key);
+    if (it != cse.end()) return it->second;
+
+    BlockNode n;
+    n.kind = BKind::Pbs;
+    n.vset = O;
+    n.noise2 = 1.f;
+    n.lut = lid;
+    n.terms = terms;
+    n.cst = c;
+    n.level = 1 + level_of(terms, false);
+    nodes.push_back(n);
+    n_pbs_nodes++;
+    const BlockId id = (BlockId)nodes.size() - 1;
+    cse[key] = id;
+    return id;
+}
+
+// f(x, y) over clean 2-bit block values; one operand trivial -> univariate LUT on the other
+BlockId Graph::bivar(BlockId x, BlockId y, const std::function<int(int, int)>& f) {
+    const bool tx = is_trivial(x), ty = is_trivial(y);
+    if (tx && ty) return trivial_block(f(trivial_value(x), trivial_value(y)));
+    if (((tx ? 0u : nodes[x].vset) | (ty ? 0u : nodes[y].vset)) & ~0xFu) fail("bivariate operand is not a clean 2-bit block");
+    if (tx) {
+        const int cx = trivial_value(x);
+        return pbs({{y, 1}}, 0, table_of([&](int v) { return f(cx, v & 3); }));
+    }
+    if (ty) {
+        const int cy = trivial_value(y);
+        return pbs({{x, 1}}, 0, table_of([&](int v) { return f(v & 3, cy); }));
+    }
+    return pbs({{x, 4}, {y, 1}}, 0, table_of([&](int v) { return f(v >> 2, v & 3); }));
+}
+
+// ------------------------------------------------------------------------------------ char level
+Char Graph::input_char() { return Char{input_block(), input_block(), input_block(), input_block()}; }
+
+Char Graph::trivial_char(uint8_t v) {
+    return Char{trivial_block(v & 3), trivial_block((v >> 2) & 3), trivial_block((v >> 4) & 3), trivial_block((v >> 6) & 3)};
+}
+
+Char Graph::flag_char(BlockId b) { return Char{b, trivial_block(0), trivial_block(0), trivial_block(0)}; }
+
+Char Graph::eq(const Char& a, const Char& b) {
+    std::vector<std::pair<BlockId, int>> s;
+    for (int i = 0; i < 4; i++) s.push_back({bivar(a[i], b[i], [](int x, int y) { return x == y; }), 1});
+    return flag_char(pbs(s, 0, table_of([](int v) { return v == 4; })));
+}
+
+Char Graph::ne(const Char& a, const Char& b) {
+    std::vector<std::pair<BlockId, int>> s;
+    for (int i = 0; i < 4; i++) s.push_back({bivar(a[i], b[i], [](int x, int y) { return x != y; }), 1});
+    return flag_char(pbs(s, 0, table_of([](int v) { return v != 0; })));
+}
+
+// op: 0 lt, 1 le, 2 gt, 3 ge.  Pairs of blocks are packed lo + 4 hi, subtracted raw (the difference
+// lives in [-15, 15]: negative values carry the padding bit, so the nz LUT returns -1 for them),
+// sign = nz(diff) + 1 in {0:<, 1:=, 2:>}; the two signs are merged by one more LUT.
+Char Graph::cmp(const Char& a, const Char& b, int op) {
+    BlockId p[2];
+    {
+        SignedScope sc(signed_ok);
+        for (int j = 0; j < 2; j++)
+            p[j] = pbs({{a[2 * j], 1}, {a[2 * j + 1], 4}, {b[2 * j], -1}, {b[2 * j + 1], -4}}, 0,
+                       table_of([](int v) { return v != 0; }));
+    }
+    auto fin = table_of([op](int v) {
+        const int hi = v >> 2, lo = v & 3;
+        const int r = (hi == 1) ? lo : hi;
+        switch (op) {
+            case 0: return (int)(r == 0);
+            case 1: return (int)(r != 2);
+            case 2: return (int)(r == 2);
+            default: return (int)(r != 0);
+        }
+    });
+    return flag_char(pbs({{p[1], 4}, {p[0], 1}}, 5, fin));
+}
+Char Graph::lt(const Char& a, const Char& b) { return cmp(a, b, 0); }
+Char Graph::le(const Char& a, const Char& b) { return cmp(a, b, 1); }
+Char Graph::gt(const Char& a, const Char& b) { return cmp(a, b, 2); }
+Char Graph::ge(const Char& a, const Char& b) { return cmp(a, b, 3); }
+
+Char Graph::bitand_(const Char& a, const Char& b) {
+    Char r;
+    for (int i = 0; i < 4; i++) r[i] = bivar(a[i], b[i], [](int x, int y) { return x & y; });
+    return r;
+}
+Char Graph::bitor_(const Char& a, const Char& b) {
+    Char r;
+    for (int i = 0; i < 4; i++) r[i] = bivar(a[i], b[i], [](int x, int y) { return x | y; });
+    return r;
+}
+
+// sequential carry propagation over 4 blocks (the path tfhe-rs takes for <= 4 blocks, A.10); a block
+// whose carry is the same for every reachable value needs no PBS at all
+std::array<BlockId, 4> Graph::propagate(std::array<BlockId, 4> s) {
+    std::array<BlockId, 4> m;
+    BlockId carry = trivial_block(0);
+    for (int i = 0; i < 4; i++) {
+        const BlockId cur = lin({{s[i], 1}, {carry, 1}}, 0);
+        const uint32_t S = nodes[cur].vset;
+        if (S >> 16) { fail("carry propagation input overflows the block"); m[i] = cur; continue; }
+        uint32_t carries = 0, msgs = 0;
+        for (int v = 0; v < 16; v++) if (S >> v & 1) { carries |= 1u << (v >> 2); msgs |= 1u << (v & 3); }
+        if (popcount32(carries) == 1) {
+            const int cv = __builtin_ctz(carries);
+            m[i] = lin({{cur, 1}}, -4 * cv, msgs);
+            carry = trivial_block(cv);
+        } else {
+            m[i] = pbs({{cur, 1}}, 0, table_of([](int v) { return v & 3; }));
+            carry = (i < 3) ? pbs({{cur, 1}}, 0, table_of([](int v) { return v >> 2; })) : trivial_block(0);
+        }
+    }
+    return m;
+}
+
+Char Graph::add(const Char& a, const Char& b) {
+    std::array<BlockId, 4> s;
+    for (int i = 0; i < 4; i++) s[i] = lin({{a[i], 1}, {b[i], 1}}, 0);
+    return propagate(s);
+}
+
+// a - b mod 256: blocks a_i + (4 - b_i) with the borrowed 4 taken back from the next block
+Char Graph::sub(const Char& a, const Char& b) {
+    std::array<BlockId, 4> s;
+    for (int i = 0; i < 4; i++) s[i] = lin({{a[i], 1}, {b[i], -1}}, i == 0 ? 4 : 3);
+    return propagate(s);
+}
+
+BlockId Graph::cond_bit(const Char& c) {
+    std::vector<std::pair<BlockId, int>> live;
+    for (int i = 0; i < 4; i++) {
+        if (is_trivial(c[i])) { if (trivial_value(c[i]) != 0) return trivial_block(1); }
+        else live.push_back({c[i], 1});
+    }
+    if (live.empty()) return trivial_block(0);
+    if (live.size() == 1 && !(nodes[live[0].first].vset & ~0x3u)) return live[0].first;
+    return pbs(live, 0, table_of([](int v) { return v != 0; }));
+}
+
+// scalar_ne(cond, 0) then a CMUX per block: keep_if(4 t + c) + zero_if(4 f + c)
+Char Graph::if_then_else(const Char& c, const Char& t, const Char& f) {
+    const BlockId cb = cond_bit(c);
+    if (is_trivial(cb)) return trivial_value(cb) ? t : f;
+    Char r;
+    for (int i = 0; i < 4; i++) {
+        if (t[i] == f[i]) { r[i] = t[i]; continue; }
+        const BlockId k = bivar(t[i], cb, [](int x, int cnd) { return (cnd & 1) ? x : 0; });
+        const BlockId z = bivar(f[i], cb, [](int x, int cnd) { return (cnd & 1) ? 0 : x; });
+        r[i] = lin({{k, 1}, {z, 1}}, 0, (nodes[t[i]].vset | nodes[f[i]].vset) & 0xF);
+    }
+    return r;
+}
+
+Char Graph::is_whitespace(const Char& a) {
+    Char r = eq(a, trivial_char(0x20));
+    for (uint8_t w : {0x09, 0x0A, 0x0B, 0x0C, 0x0D}) r = bitor_(r, eq(a, trivial_char(w)));
+    return r;
+}
+Char Graph::is_uppercase(const Char& a) { return bitand_(ge(a, trivial_char(0x41)), le(a, trivial_char(0x5A))); }
+Char Graph::is_lowercase(const Char& a) { return bitand_(ge(a, trivial_char(0x61)), le(a, trivial_char(0x7A))); }
+Char Graph::flip(const Char& a) { return sub(trivial_char(1), a); }
+
+// ---- wide reductions (plaintext-identical to chains of bitand / bitor / add on 0/1 chars)
+static const int kChunk = 15;
+
+Char Graph::and_all(const std::vector<Char>& flags) {
+    std::vector<BlockId> cur;
+    for (auto& c : flags) cur.push_back(cond_bit(c));
+    if (cur.empty()) return trivial_char(1);
+    while (cur.size() > 1) {
+        std::vector<BlockId> nxt;
+        for (size_t i = 0; i < cur.size(); i += kChunk) {
+            const size_t k = std::min<size_t>(kChunk, cur.size() - i);
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
+            nxt.push_back(pbs(ops, 0, table_of([k](int v) { return v == (int)k; })));
+        }
+        cur.swap(nxt);
+    }
+    return flag_char(cur[0]);
+}
+
+Char Graph::or_all(const std::vector<Char>& flags) {
+    std::vector<BlockId> cur;
+    for (auto& c : flags) cur.push_back(cond_bit(c));
+    if (cur.empty()) return trivial_char(0);
+    while (cur.size() > 1) {
+        std::vector<BlockId> nxt;
+        for (size_t i = 0; i < cur.size(); i += kChunk) {
+            const size_t k = std::min<size_t>(kChunk, cur.size() - i);
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
+            nxt.push_back(pbs(ops, 0, table_of([](int v) { return v != 0; })));
+        }
+        cur.swap(nxt);
+    }
+    return flag_char(cur[0]);
+}
+
+// column compression: each column holds blocks of weight 4^c; chunks whose maximum sum is <= 15 are
+// replaced by (sum & 3) in the same column and (sum >> 2) in the next one
+Char Graph::sum_flags(const std::vector<Char>& flags) {
+    std::vector<std::vector<BlockId>> col(5);
+    for (auto& c : flags) col[0].push_back(cond_bit(c));
+    auto vmax = [&](BlockId b) { int m = 0; for (int v = 0; v < 16; v++) if (nodes[b].vset >> v & 1) m = v; return m; };
+    for (int guard = 0; guard < 64; guard++) {
+        bool busy = false;
+        std::vector<std::vector<BlockId>> nxt(5);
+        for (int c = 0; c < 4; c++) {
+            if (col[c].size() <= 1) { for (auto b : col[c]) nxt[c].push_back(b); continue; }
+            busy = true;
+            size_t i = 0;
+            while (i < col[c].size()) {
+                std::vector<std::pair<BlockId, int>> ops;
+                int total = 0;
+                while (i < col[c].size() && total + vmax(col[c][i]) <= 15 && ops.size() < FHESTR_MAX_TERMS) {
+                    total += vmax(col[c][i]);
+                    ops.push_back({col[c][i], 1});
+                    i++;
+                }
+                if (ops.size() == 1) { nxt[c].push_back(ops[0].first); continue; }
+                const BlockId m = pbs(ops, 0, table_of([](int v) { return v & 3; }));
+                nxt[c].push_back(m);
+                if (c < 3 && total >= 4) nxt[c + 1].push_back(pbs(ops, 0, table_of([](int v) { return v >> 2; })));
+            }
+        }
+        // trivial blocks in a column fold into one constant; keep them as they are (lin folds them)
+        col.swap(nxt);
+        if (!busy) break;
+    }
+    Char r;
+    for (int c = 0; c < 4; c++) {
+        if (col[c].empty()) r[c] = trivial_block(0);
+        else r[c] = col[c][0];
+    }
+    // a single survivor per column may still be > 3 only if it never went through a PBS (a lone flag): fine
+    return r;
+}
+
+
+Char Graph::nonzero(const Char& a) { return flag_char(cond_bit(a)); }
+
+Char Graph::block_and_eq(const std::vector<std::pair<Char, Char>>& pairs) {
+    std::vector<Char> flags;
+    for (auto& pr : pairs)
+        for (int i = 0; i < 4; i++)
+            flags.push_back(flag_char(bivar(pr.first[i], pr.second[i], [](int x, int y) { return x == y; })));
+    return and_all(flags);
+}
+
+// first_i = m_i AND no earlier flag.  Inside a chunk of <= 15 flags: u = sum_{k<i} m_k - m_i + 1 is 0
+// exactly for the first set flag; chunks are ranked the same way on their ANY flags, recursively.
+std::vector<Char> Graph::first_one_hot(const std::vector<Char>& flags, Char* any) {
+    const size_t n = flags.size();
+    std::vector<BlockId> m;
+    for (auto& c : flags) m.push_back(cond_bit(c));
+    auto is_zero_tab = table_of([](int v) { return v == 0; });
+    auto first_in = [&](const std::vector<BlockId>& v) {
+        std::vector<BlockId> out;
+        for (size_t i = 0; i < v.size(); i++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t k = 0; k < i; k++) ops.push_back({v[k], 1});
+            ops.push_back({v[i], -1});
+            out.push_back(pbs(ops, 1, is_zero_tab));
+        }
+        return out;
+    };
+    std::vector<Char> res;
+    if (n <= (size_t)kChunk) {
+        for (auto b : first_in(m)) res.push_back(flag_char(b));
+        if (any) {
+            std::vector<Char> tmp;
+            for (auto b : m) tmp.push_back(flag_char(b));
+            *any = or_all(tmp);
+        }
+        return res;
+    }
+    std::vector<Char> chunk_any;
+    std::vector<std::vector<BlockId>> local;
+    for (size_t i = 0; i < n; i += kChunk) {
+        std::vector<BlockId> ch(m.begin() + i, m.begin() + std::min(n, i + kChunk));
+        std::vector<Char> tmp;
+        for (auto b : ch) tmp.push_back(flag_char(b));
+        chunk_any.push_back(or_all(tmp));
+        local.push_back(first_in(ch));
+    }
+    std::vector<Char> chunk_first = first_one_hot(chunk_any, any);
+    for (size_t c = 0; c < local.size(); c++)
+        for (auto b : local[c])
+            res.push_back(flag_char(bivar(b, chunk_first[c][0], [](int x, int y) { return x & y & 1; })));
+    return res;
+}
+
+Char Graph::select_by_one_hot(const std::vector<Char>& onehot, const std::vector<uint8_t>& values, const Char& none,
+                              uint8_t none_value) {
+    // per block: digit = 1*[any flag whose digit is 1] + 2*[... is 2] + 3*[... is 3]; the three class flags
+    // are OR trees (the flags are one-hot, so at most one class fires) and the result is a clean digit
+    Char r;
+    for (int blk = 0; blk < 4; blk++) {
+        std::vector<std::pair<BlockId, int>> ops;
+        for (int d = 1; d <= 3; d++) {
+            std::vector<Char> cls;
+            for (size_t i = 0; i < onehot.size(); i++)
+                if (((values[i] >> (2 * blk)) & 3) == d) cls.push_back(onehot[i]);
+            if (((none_value >> (2 * blk)) & 3) == d) cls.push_back(none);
+            if (cls.empty()) continue;
+            ops.push_back({or_all(cls)[0], d});
+        }
+        r[blk] = lin(ops, 0, 0xF);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------ compile
+bool Graph::compile(CompiledProgram& out, std::string& err) {
+    if (!error.empty()) { err = error; return false; }
+    out = CompiledProgram();
+    // reachability from the outputs
+    std::vector<char> live(nodes.size(), 0);
+    std::vector<BlockId> stack;
+    for (auto b : outputs) {
+        if (nodes[b].kind == BKind::Linear) nodes[b].materialized = true;
+        if (!live[b]) { live[b] = 1; stack.push_back(b); }
+    }
+    while (!stack.empty()) {
+        const BlockId b = stack.back();
+        stack.pop_back();
+        for (auto& t : nodes[b].terms)
+            if (!live[t.blk]) { live[t.blk] = 1; stack.push_back(t.blk); }
+    }
+    // inputs keep their creation order in slots [0, n_inputs) whether live or not (callers upload by index)
+    uint32_t slot = 0;
+    for (size_t b = 0; b < nodes.size(); b++)
+        if (nodes[b].kind == BKind::Input) nodes[b].slot = (int32_t)slot++;
+    out.n_inputs = slot;
+    for (auto b : outputs)
+        if (nodes[b].kind == BKind::Trivial && nodes[b].slot < 0) {
+            nodes[b].slot = (int32_t)slot++;
+            out.trivial_slots.push_back({(uint32_t)nodes[b].slot, (uint8_t)nodes[b].cst});
+        }
+    int depth = 0;
+    for (size_t b = 0; b < nodes.size(); b++) if (live[b]) depth = std::max(depth, (int)nodes[b].level);
+    std::vector<std::vector<BlockId>> pbs_at(depth + 1), lin_at(depth + 1);
+    for (size_t b = 0; b < nodes.size(); b++) {
+        if (!live[b]) continue;
+        if (nodes[b].kind == BKind::Pbs) pbs_at[nodes[b].level].push_back((BlockId)b);
+        else if (nodes[b].kind == BKind::Linear && nodes[b].materialized) lin_at[nodes[b].level].push_back((BlockId)b);
+    }
+    for (int l = 0; l <= depth; l++) {
+        for (auto b : pbs_at[l]) nodes[b].slot = (int32_t)slot++;
+        for (auto b : lin_at[l]) nodes[b].slot = (int32_t)slot++;
+    }
+    out.n_slots = slot;
+    auto emit = [&](BlockId b) {
+        const BlockNode& n = nodes[b];
+        fhestr_job j;
+        memset(&j, 0, sizeof j);
+        j.dst = (uint32_t)n.slot;
+        j.lut = n.kind == BKind::Pbs ? n.lut : -1;
+        j.n_terms = (uint32_t)n.terms.size();
+        for (size_t t = 0; t < n.terms.size(); t++) {
+            const BlockNode& s = nodes[n.terms[t].blk];
+            if (s.slot < 0) { err = "internal: job source has no slot"; return false; }
+            j.src[t] = (uint32_t)s.slot;
+            j.coeff[t] = n.terms[t].coeff;
+        }
+        j.constant = ((uint64_t)mod32(n.cst)) << delta_log;
+        out.jobs.push_back(j);
+        return true;
+    };
+    out.level_offsets.push_back(0);
+    for (int l = 0; l <= depth; l++) {
+        if (pbs_at[l].empty() && lin_at[l].empty()) continue;
+        out.level_first_dst.push_back(pbs_at[l].empty() ? 0u : (uint32_t)nodes[pbs_at[l][0]].slot);
+        for (auto b : pbs_at[l]) if (!emit(b)) return false;
+        for (auto b : lin_at[l]) if (!emit(b)) return false;
+        out.level_pbs.push_back((uint32_t)pbs_at[l].size());
+        out.n_pbs += pbs_at[l].size();
+        out.level_offsets.push_back((uint32_t)out.jobs.size());
+    }
+    return true;
+}
+
+}  // namespace fhestr

@@ -1,0 +1,143 @@
+// graph.h -- host-side op graph: the 11 per-character primitives of the reference
+// (/root/reference/src/ciphertext/fheasciichar.rs:17-168) recorded as radix-block PBS jobs, then
+// flattened into dependency levels of independent jobs for the batched engine.
+//
+// This replaces what tfhe-rs' integer::ServerKey does behind those primitives: the
+// per-op recipes over 4 blocks of 2 message + 2 carry bits, expressed with 16-entry LUTs over
+// `sum coeff*block + const`.  It is pure host code (no CUDA): tests interpret the compiled job list on
+// plaintext block values, the engine executes the same list on ciphertexts.
+//
+// Every block carries, on the host only:
+//   vset    the set of plaintext values (mod 32, bit 4 = padding bit) the block can hold.  A PBS whose
+//           output set is a single value is folded to a trivial constant (this subsumes tfhe-rs'
+//           trivial-ciphertext short cut and constant propagation through flag logic);
+//   noise2  squared 2-norm of the block as a combination of fresh PBS outputs.  The largest value the
+//           reference's own recipes reach is 34 (comparison: raw subtraction of two packed pairs
+//           (lo + 4 hi) - (lo' + 4 hi')); a refresh PBS is inserted before that would be exceeded;
+//   level   PBS depth at which the value exists.
+#pragma once
+#include <stdint.h>
+
+#include <array>
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fhestr_engine.h"
+
+namespace fhestr {
+
+typedef uint32_t BlockId;
+typedef std::array<BlockId, 4> Char;  // little-endian base-4 digits of a u8
+
+struct Term {
+    BlockId blk;
+    int32_t coeff;
+};
+
+enum class BKind : uint8_t { Trivial, Input, Pbs, Linear };
+
+struct BlockNode {
+    BKind kind = BKind::Trivial;
+    bool materialized = false;   // Linear only: has its own arena slot (acts as an atom)
+    uint32_t vset = 1;           // bit v set <=> value v (mod 32) possible
+    float noise2 = 0.f;
+    int32_t level = 0;
+    int32_t lut = -1;            // Pbs: graph-local LUT id
+    std::vector<Term> terms;     // Pbs input / Linear definition, over atoms only
+    int32_t cst = 0;             // constant in units of delta (mod 32)
+    int32_t slot = -1;           // arena slot, assigned by compile()
+};
+
+struct CompiledProgram {
+    std::vector<fhestr_job> jobs;          // level by level; PBS jobs before leveled jobs inside a level
+    std::vector<uint32_t> level_offsets;   // n_levels + 1
+    std::vector<uint32_t> level_pbs;       // PBS jobs per level
+    std::vector<uint32_t> level_first_dst; // first arena slot written by the PBS jobs of a level (contiguous)
+    uint32_t n_slots = 0;
+    uint32_t n_inputs = 0;                 // input blocks occupy slots [0, n_inputs)
+    uint64_t n_pbs = 0;
+    std::vector<std::pair<uint32_t, uint8_t>> trivial_slots;  // (slot, value) to initialise
+};
+
+class Graph {
+public:
+    static constexpr float kNoise2Limit = 34.0f;
+    int delta_log = 59;
+
+    // ---- block level
+    BlockId trivial_block(int value);            // value mod 32
+    BlockId input_block();
+    BlockId lin(const std::vector<std::pair<BlockId, int>>& ops, int cst, uint32_t declared_vset = 0);
+    BlockId pbs(const std::vector<std::pair<BlockId, int>>& ops, int cst, const std::array<uint8_t, 16>& table);
+    BlockId bivar(BlockId x, BlockId y, const std::function<int(int, int)>& f);  // f over 2-bit x 2-bit... see .cpp
+    BlockId refresh(BlockId b);
+    bool is_trivial(BlockId b) const { return nodes[b].kind == BKind::Trivial; }
+    int trivial_value(BlockId b) const;
+    const BlockNode& node(BlockId b) const { return nodes[b]; }
+
+    // ---- the reference's primitives (fheasciichar.rs)
+    Char input_char();
+    Char trivial_char(uint8_t v);                     // :17-25
+    Char eq(const Char& a, const Char& b);            // :35
+    Char ne(const Char& a, const Char& b);            // :40
+    Char le(const Char& a, const Char& b);            // :45
+    Char lt(const Char& a, const Char& b);            // :50
+    Char ge(const Char& a, const Char& b);            // :55
+    Char gt(const Char& a, const Char& b);            // :60
+    Char bitand_(const Char& a, const Char& b);       // :65
+    Char bitor_(const Char& a, const Char& b);        // :74
+    Char sub(const Char& a, const Char& b);           // :83
+    Char add(const Char& a, const Char& b);           // :87
+    Char if_then_else(const Char& c, const Char& t, const Char& f);  // :93
+    Char is_whitespace(const Char& a);                // :106
+    Char is_uppercase(const Char& a);                 // :132
+    Char is_lowercase(const Char& a);                 // :146
+    Char flip(const Char& a);                         // :161
+    // plaintext-equivalent wide reductions used by the depth-minimised string algorithms
+    Char and_all(const std::vector<Char>& flags);     // AND of 0/1 chars, tree of sum + is_k LUTs
+    Char or_all(const std::vector<Char>& flags);      // OR  of 0/1 chars, tree of sum + nz LUTs
+    Char sum_flags(const std::vector<Char>& flags);   // u8 sum (mod 256) of 0/1 chars
+    Char nonzero(const Char& a);                      // a != 0 as one PBS over the block sum
+    Char block_and_eq(const std::vector<std::pair<Char, Char>>& pairs);  // AND_i (a_i == b_i), block level
+    // one-hot of the first set flag (all zero if none) -- replaces priority-select chains
+    std::vector<Char> first_one_hot(const std::vector<Char>& flags, Char* any);
+    // u8 value sum_i onehot_i * value_i + (none ? none_value : 0), refreshed to clean blocks
+    Char select_by_one_hot(const std::vector<Char>& onehot, const std::vector<uint8_t>& values, const Char& none, uint8_t none_value);
+
+    // ---- compile
+    void mark_output(const Char& c) { for (auto b : c) outputs.push_back(b); }
+    // returns false and fills error on failure
+    bool compile(CompiledProgram& out, std::string& error);
+    int slot_of(BlockId b) const { return nodes[b].slot; }
+    const std::vector<std::array<uint8_t, 16>>& luts() const { return lut_tables; }
+    uint64_t pbs_recorded() const { return n_pbs_nodes; }
+
+    std::string error;  // sticky: first recording error (bad value range, ...)
+
+private:
+    std::vector<BlockNode> nodes;
+    std::vector<BlockId> outputs;
+    std::vector<std::array<uint8_t, 16>> lut_tables;
+    std::map<std::array<uint8_t, 16>, int> lut_ids;
+    std::unordered_map<std::string, BlockId> cse;
+    BlockId triv_cache[32];
+    bool triv_cache_init = false;
+    uint64_t n_pbs_nodes = 0;
+
+    int lut_id(const std::array<uint8_t, 16>& t);
+    void flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, std::vector<Term>& terms, int& out_cst);
+    uint32_t vset_of(const std::vector<std::pair<BlockId, int>>& ops, int cst) const;
+    float noise2_of(const std::vector<Term>& terms) const;
+    int level_of(const std::vector<Term>& terms, bool for_linear) const;
+    bool signed_ok = false;
+    void fail(const std::string& m) { if (error.empty()) error = m; }
+    Char cmp(const Char& a, const Char& b, int op);
+    Char flag_char(BlockId b);
+    std::array<BlockId, 4> propagate(std::array<BlockId, 4> s);
+    BlockId cond_bit(const Char& c);
+};
+
+}  // namespace fhestr

@@ -1,0 +1,95 @@
+#!/usr/bin/env python3
+"""Write reference_tests.json: the literal inputs of the reference's own unit tests
+(/root/reference/src/main.rs:138-1153, non-split methods) with the value Rust `std` gives on them --
+which is what each reference test asserts against.  `std` results are spelled out with the Python
+expression that has the same meaning on these ASCII inputs; nothing here touches the oracle.
+
+Each case: name (test fn), line (main.rs line of the fn), method, args, padding (of the first string;
+second strings of two-string tests use the same), expect.
+Run: python tests/golden/make_reference_tests.py
+"""
+import json
+import os
+
+WS = " \t\n\r\x0b\x0c"
+C = []
+
+
+def add(name, line, method, args, padding, expect):
+    C.append(dict(name=name, line=line, method=method, args=args, padding=padding, expect=expect))
+
+
+add("valid_contains", 139, "contains", ["awesomezamaisawesome", "zama"], 3, int("zama" in "awesomezamaisawesome"))
+add("invalid_contains", 158, "contains", ["hello world", "zama"], 3, int("zama" in "hello world"))
+add("invalid_ends_with", 177, "ends_with", ["hello world", "zama"], 1, int("hello world".endswith("zama")))
+add("valid_starts_with", 200, "starts_with", ["hello world", "hello"], 1, int("hello world".startswith("hello")))
+add("invalid_starts_with", 223, "starts_with", ["hello world", "zama"], 1, int("hello world".startswith("zama")))
+add("valid_ends_with", 246, "ends_with", ["hello world", "world"], 1, int("hello world".endswith("world")))
+add("uppercase", 269, "to_upper", ["zama IS awesome"], 1, "zama IS awesome".upper())
+add("repeat", 289, "repeat", ["abc", 3], 1, "abc" * 3)
+add("replace1", 311, "replace", ["hello world world test", "world", "abc"], 1, "hello world world test".replace("world", "abc"))
+add("replace2", 336, "replace", ["hello abc abc test", "abc", "world"], 1, "hello abc abc test".replace("abc", "world"))
+add("replacen", 361, "replacen", ["hello abc abc test", "abc", "world", 1], 1, "hello abc abc test".replace("abc", "world", 1))
+add("lowercase", 388, "to_lower", ["zama IS awesome"], 1, "zama IS awesome".lower())
+add("trim_end", 408, "trim_end", ["ZA MA\n\t \r\x0c"], 1, "ZA MA\n\t \r\x0c".rstrip(WS))
+add("do_not_trim_end", 428, "trim_end", ["\nZA MA"], 1, "\nZA MA".rstrip(WS))
+add("trim_start", 448, "trim_start", ["\nZA MA"], 1, "\nZA MA".lstrip(WS))
+add("trim", 468, "trim", ["\nZA MA\n"], 1, "\nZA MA\n".strip(WS))
+add("is_empty", 488, "is_empty", [""], 1, int(len("") == 0))
+add("is_not_empty", 507, "is_empty", ["hello"], 1, int(len("hello") == 0))
+add("len", 526, "len", ["hello world"], 1, len("hello world"))
+add("rfind", 547, "rfind", ["hello abc abc test", "abc"], 1, "hello abc abc test".rfind("abc"))
+add("invalid_rfind", 570, "rfind", ["hello test", "abc"], 1, 255)  # asserts MAX_FIND_LENGTH
+add("unsupported_size_rfind", 596, "rfind", ["hello test" * 100, "abc"], 1, "panic: Maximum supported size for find reached")
+add("find", 614, "find", ["hello test", "test"], 1, "hello test".find("test"))
+add("eq", 637, "eq", ["hello test", "hello test"], 1, int("hello test" == "hello test"))
+add("eq_ignore_case", 664, "eq_ignore_case", ["hello TEST", "hello test"], 1, int("hello TEST".lower() == "hello test".lower()))
+s = "HELLO test test HELLO"
+add("strip_prefix", 691, "strip_prefix", [s, "HELLO"], 1, [s[len("HELLO"):], 1])
+add("strip_suffix", 714, "strip_suffix", [s, "HELLO"], 1, [s[:-len("HELLO")], 1])
+add("dont_strip_suffix", 738, "strip_suffix", [s, "WORLD"], 1, [s, 0])
+add("dont_strip_prefix", 765, "strip_prefix", [s, "WORLD"], 1, [s, 0])
+add("concatenate", 793, "concatenate", ["Hello, ", "World!"], 1, "Hello, " + "World!")
+add("less_than", 819, "lt", ["aaa", "aaaa"], 1, int("aaa" < "aaaa"))
+add("less_equal", 847, "le", ["aaa", "aaaa"], 1, int("aaa" <= "aaaa"))
+add("greater_than", 875, "gt", ["aaa", "aaaa"], 1, int("aaa" > "aaaa"))
+add("greater_equal", 903, "ge", ["aaa", "aaaa"], 1, int("aaa" >= "aaaa"))
+
+# the CLI self-check of BASELINE config 1 (src/main.rs:47-100, src/utils.rs:122-718):
+# --string hello --pattern ello --n 1 --from ello --to _llo, STRING_PADDING = 1
+cli = dict(string="hello", pattern="ello", n=1, frm="ello", to="_llo")
+h, p, n, f, t = cli["string"], cli["pattern"], cli["n"], cli["frm"], cli["to"]
+CLI = [
+    ("Contains", "contains", [h, p], int(p in h)),
+    ("EndsWith", "ends_with", [h, p], int(h.endswith(p))),
+    ("EqIgnoreCase", "eq_ignore_case", [h, p], int(h.lower() == p.lower())),
+    ("Find", "find", [h, p], h.find(p) if p in h else 255),
+    ("IsEmpty", "is_empty", [h], int(h == "")),
+    ("Len", "len", [h], len(h)),
+    ("Repeat", "repeat", [h, n], h * n),
+    ("Replace", "replace", [h, f, t], h.replace(f, t)),
+    ("ReplaceN", "replacen", [h, f, t, n], h.replace(f, t, n)),
+    ("Rfind", "rfind", [h, p], h.rfind(p) if p in h else 255),
+    ("StartsWith", "starts_with", [h, p], int(h.startswith(p))),
+    ("StripPrefix", "strip_prefix", [h, p], [h[len(p):] if h.startswith(p) else h, int(h.startswith(p))]),
+    ("StripSuffix", "strip_suffix", [h, p], [h[:-len(p)] if h.endswith(p) else h, int(h.endswith(p))]),
+    ("ToLower", "to_lower", [h], h.lower()),
+    ("ToUpper", "to_upper", [h], h.upper()),
+    ("Trim", "trim", [h], h.strip(WS)),
+    ("TrimEnd", "trim_end", [h], h.rstrip(WS)),
+    ("TrimStart", "trim_start", [h], h.lstrip(WS)),
+    ("Concatenate", "concatenate", [h, p], h + p),
+    ("Lt", "lt", [h, p], int(h < p)),
+    ("Le", "le", [h, p], int(h <= p)),
+    ("Gt", "gt", [h, p], int(h > p)),
+    ("Ge", "ge", [h, p], int(h >= p)),
+    ("Eq", "eq", [h, p], int(h == p)),
+    ("Ne", "ne", [h, p], int(h != p)),
+]
+for nm, method, args, expect in CLI:
+    add("cli_" + nm, 47, method, args, 1, expect)
+
+out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_tests.json")
+with open(out, "w") as fjson:
+    json.dump(C, fjson, indent=1)
+print("wrote", out, len(C), "cases")
