@@ -9,8 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfhestr_engine.so")
-SOURCES = ["engine.cu", "blind_rotate.cu", "keyswitch.cu", "aux_kernels.cu", "client.cpp", "graph.cpp"]  # graph.cpp: host-side op graph (optional until present)
-HEADERS = ["kernels.cuh", "br_core.cuh", "fft32_gen.cuh", "graph.h", os.path.join("..", "..", "include", "fhestr_engine.h")]
+SOURCES = ["engine.cu", "blind_rotate.cu", "keyswitch.cu", "aux_kernels.cu", "client.cpp", "graph.cpp", "strings.cpp", "graph_capi.cpp"]
+HEADERS = ["kernels.cuh", "br_core.cuh", "fft32_gen.cuh", "graph.h", "strings.h", os.path.join("..", "..", "include", "fhestr_engine.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
-        subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"])
+        subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-ldl"])
     return LIB
 
 

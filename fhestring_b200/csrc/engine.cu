@@ -2,6 +2,7 @@
 // ciphertext arena, LUT registry and the batched-PBS launch path.  No CPU fallback anywhere: if CUDA
 // is not usable every entry point fails with an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstring>
@@ -43,14 +44,52 @@ struct fhestr_engine {
     bool timing = false;
     struct Timed { cudaEvent_t a, b, c; uint32_t pbs; };   // a..b keyswitch, b..c blind rotation
     std::vector<Timed> timed;
+    // multi-GPU (one process per GPU): NCCL communicator, resolved at run time from libnccl.so.2
+    void* comm = nullptr;
+    uint32_t rank = 0, world = 1;
     std::string err;
 };
+
+// ---- NCCL, bound with dlopen so that the library has no link-time dependency on it: inside a torch
+// process this resolves to the libnccl.so.2 torch already loaded, otherwise to the system one.
+namespace {
+struct NcclUid { char b[128]; };  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.lib) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    return api;
+}
+constexpr int kNcclUint64 = 5;  // ncclUint64 in nccl.h
+}  // namespace
 
 struct fhestr_program {
     fhestr_engine* eng = nullptr;
     fhestr_job* d_jobs = nullptr;          // all jobs, PBS jobs of a level first, then its leveled jobs
     std::vector<uint32_t> level_off;       // n_levels + 1
     std::vector<uint32_t> level_pbs;       // PBS jobs in each level (the rest are leveled)
+    std::vector<uint32_t> level_first_dst; // dst of the level's first PBS job
+    std::vector<uint8_t> level_contiguous; // PBS job i of the level writes first_dst + i (needed to shard it)
     uint32_t max_level_pbs = 0;
 };
 
@@ -162,6 +201,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    if (e->comm) fhestr_comm_destroy(e);
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
     cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
@@ -327,6 +367,11 @@ int fhestr_program_create(fhestr_engine* e, const fhestr_job* jobs, const uint32
         const uint32_t a = level_offsets[l], b = level_offsets[l + 1];
         p->level_pbs[l] = partition_jobs(jobs + a, b - a, sorted.data() + a);
         if (p->level_pbs[l] > p->max_level_pbs) p->max_level_pbs = p->level_pbs[l];
+        uint8_t contiguous = 1;
+        for (uint32_t i = 1; i < p->level_pbs[l]; i++)
+            if (sorted[a + i].dst != sorted[a].dst + i) { contiguous = 0; break; }
+        p->level_first_dst.push_back(p->level_pbs[l] ? sorted[a].dst : 0u);
+        p->level_contiguous.push_back(contiguous);
     }
     cudaError_t ce = cudaMalloc(&p->d_jobs, (size_t)(total ? total : 1) * sizeof(fhestr_job));
     if (ce == cudaSuccess)
@@ -354,23 +399,35 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
     CK(cudaSetDevice(e->device));
     int rc = ensure_scratch(e, p->max_level_pbs);
     if (rc) return rc;
+    if (world > 1 && (!e->comm || e->world != world || e->rank != rank))
+        return fail(e, FHESTR_E_STATE, "multi-rank run needs fhestr_comm_init with the same rank/world");
     for (uint32_t l = first_level; l < last_level; l++) {
         const uint32_t a = p->level_off[l], n_all = p->level_off[l + 1] - a, n_pbs = p->level_pbs[l];
-        // shard the PBS jobs of the level across ranks (contiguous slices); leveled jobs are cheap and
-        // replicated on every rank so that no exchange is needed for them
-        const uint32_t per = (n_pbs + world - 1) / world;
-        const uint32_t lo = per * rank < n_pbs ? per * rank : n_pbs;
-        const uint32_t hi = lo + per < n_pbs ? lo + per : n_pbs;
         if (world == 1) {
             rc = run_level(e, p->d_jobs + a, n_pbs, n_all);
-        } else {
-            rc = run_level(e, p->d_jobs + a + lo, hi - lo, hi - lo);
-            if (!rc && n_all > n_pbs) {
-                e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
-                CK(cudaGetLastError());
-            }
+            if (rc) return rc;
+            continue;
         }
-        if (rc) return rc;
+        // shard the PBS jobs of the level across ranks (equal contiguous slices, the last ones may be
+        // short or empty), all-gather the result blocks in place, then run the cheap leveled jobs
+        // replicated on every rank so that no exchange is needed for them
+        uint32_t lo, hi, per;
+        fhestr_shard_range(n_pbs, rank, world, &lo, &hi, &per);
+        if (n_pbs) {
+            const uint32_t first = p->level_first_dst[l];
+            if (!p->level_contiguous[l] || (uint64_t)first + (uint64_t)per * world > e->arena_blocks)
+                return fail(e, FHESTR_E_INVALID, "level cannot be sharded: PBS results must be contiguous and padded to a multiple of world");
+            rc = run_level(e, p->d_jobs + a + lo, hi - lo, hi - lo);
+            if (rc) return rc;
+            u64* base = e->arena + (size_t)first * (kN + 1);
+            const size_t cnt = (size_t)per * (kN + 1);
+            const int nr = nccl().AllGather(base + (size_t)rank * cnt, base, cnt, kNcclUint64, e->comm, e->stream);
+            if (nr != 0) return fail(e, FHESTR_E_CUDA, std::string("ncclAllGather: ") + (nccl().GetErrorString ? nccl().GetErrorString(nr) : "error"));
+        }
+        if (n_all > n_pbs) {
+            e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
+            CK(cudaGetLastError());
+        }
     }
     return FHESTR_OK;
 }
@@ -379,6 +436,50 @@ void fhestr_program_destroy(fhestr_program* p) {
     if (!p) return;
     cudaFree(p->d_jobs);
     delete p;
+}
+
+void fhestr_shard_range(uint32_t n_jobs, uint32_t rank, uint32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per) {
+    const uint32_t w = world ? world : 1;
+    const uint32_t p = (n_jobs + w - 1) / w;
+    const uint32_t l = (uint64_t)p * rank < n_jobs ? p * rank : n_jobs;
+    const uint32_t h = l + p < n_jobs ? l + p : n_jobs;
+    if (lo) *lo = l;
+    if (hi) *hi = h;
+    if (per) *per = p;
+}
+
+int fhestr_comm_unique_id(void* unique_id_128) {
+    if (!unique_id_128) return FHESTR_E_INVALID;
+    if (!nccl().ok) return FHESTR_E_STATE;
+    return nccl().GetUniqueId(static_cast<NcclUid*>(unique_id_128)) == 0 ? FHESTR_OK : FHESTR_E_CUDA;
+}
+
+int fhestr_comm_init(fhestr_engine* e, uint32_t rank, uint32_t world, const void* unique_id_128) {
+    if (!e || !unique_id_128 || world == 0 || rank >= world) return FHESTR_E_INVALID;
+    if (!nccl().ok) return fail(e, FHESTR_E_STATE, "libnccl.so.2 not found (dlopen)");
+    if (e->comm) return fail(e, FHESTR_E_STATE, "communicator already initialised");
+    CK(cudaSetDevice(e->device));
+    NcclUid uid;
+    memcpy(&uid, unique_id_128, sizeof uid);
+    void* comm = nullptr;
+    const int nr = nccl().CommInitRank(&comm, (int)world, uid, (int)rank);
+    if (nr != 0) return fail(e, FHESTR_E_CUDA, std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(nr) : "error"));
+    e->comm = comm;
+    e->rank = rank;
+    e->world = world;
+    return FHESTR_OK;
+}
+
+int fhestr_comm_destroy(fhestr_engine* e) {
+    if (!e) return FHESTR_E_INVALID;
+    if (e->comm) {
+        cudaStreamSynchronize(e->stream);
+        nccl().CommDestroy(e->comm);
+        e->comm = nullptr;
+        e->world = 1;
+        e->rank = 0;
+    }
+    return FHESTR_OK;
 }
 
 int fhestr_debug_keyswitch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_jobs, uint64_t* host_out) {

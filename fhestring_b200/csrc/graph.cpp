@@ -45,6 +45,9 @@ BlockId Graph::input_block() {
     n.kind = BKind::Input;
     n.vset = 0xF;  // clean message block
     n.noise2 = 1.f;
+    n.slot = (int32_t)next_slot++;  // callers upload the ciphertext to this arena slot before running
+    n.done = true;
+    n_input_nodes++;
     nodes.push_back(n);
     return (BlockId)nodes.size() - 1;
 }
@@ -387,15 +390,16 @@ Char Graph::or_all(const std::vector<Char>& flags) {
 }
 
 // column compression: each column holds blocks of weight 4^c; chunks whose maximum sum is <= 15 are
-// replaced by (sum & 3) in the same column and (sum >> 2) in the next one
-Char Graph::sum_flags(const std::vector<Char>& flags) {
-    std::vector<std::vector<BlockId>> col(5);
-    for (auto& c : flags) col[0].push_back(cond_bit(c));
+// replaced by (sum & 3) in the same column and (sum >> 2) in the next one.  Chunks are cut greedily from
+// the left, so sums over prefixes of one flag list share their leading chunks through CSE.
+std::vector<BlockId> Graph::sum_digits(const std::vector<BlockId>& flags, int ndigits) {
+    std::vector<std::vector<BlockId>> col(ndigits + 1);
+    col[0] = flags;
     auto vmax = [&](BlockId b) { int m = 0; for (int v = 0; v < 16; v++) if (nodes[b].vset >> v & 1) m = v; return m; };
     for (int guard = 0; guard < 64; guard++) {
         bool busy = false;
-        std::vector<std::vector<BlockId>> nxt(5);
-        for (int c = 0; c < 4; c++) {
+        std::vector<std::vector<BlockId>> nxt(ndigits + 1);
+        for (int c = 0; c < ndigits; c++) {
             if (col[c].size() <= 1) { for (auto b : col[c]) nxt[c].push_back(b); continue; }
             busy = true;
             size_t i = 0;
@@ -408,24 +412,122 @@ Char Graph::sum_flags(const std::vector<Char>& flags) {
                     i++;
                 }
                 if (ops.size() == 1) { nxt[c].push_back(ops[0].first); continue; }
-                const BlockId m = pbs(ops, 0, table_of([](int v) { return v & 3; }));
-                nxt[c].push_back(m);
-                if (c < 3 && total >= 4) nxt[c + 1].push_back(pbs(ops, 0, table_of([](int v) { return v >> 2; })));
+                nxt[c].push_back(pbs(ops, 0, table_of([](int v) { return v & 3; })));
+                if (c < ndigits - 1 && total >= 4) nxt[c + 1].push_back(pbs(ops, 0, table_of([](int v) { return v >> 2; })));
             }
         }
-        // trivial blocks in a column fold into one constant; keep them as they are (lin folds them)
         col.swap(nxt);
         if (!busy) break;
     }
-    Char r;
-    for (int c = 0; c < 4; c++) {
-        if (col[c].empty()) r[c] = trivial_block(0);
-        else r[c] = col[c][0];
-    }
-    // a single survivor per column may still be > 3 only if it never went through a PBS (a lone flag): fine
+    std::vector<BlockId> r(ndigits);
+    for (int c = 0; c < ndigits; c++) r[c] = col[c].empty() ? trivial_block(0) : col[c][0];
     return r;
 }
 
+Char Graph::sum_flags(const std::vector<Char>& flags) {
+    std::vector<BlockId> f;
+    for (auto& c : flags) f.push_back(cond_bit(c));
+    const std::vector<BlockId> d = sum_digits(f, 4);
+    return Char{d[0], d[1], d[2], d[3]};
+}
+
+BlockId Graph::not_flag(BlockId b) { return lin({{b, -1}}, 1, 0x3); }
+
+BlockId Graph::mul_flag(BlockId flag, BlockId blk) {
+    if (is_trivial(flag)) return trivial_value(flag) ? blk : trivial_block(0);
+    if (is_trivial(blk)) {
+        const int v = trivial_value(blk);
+        if (v == 0) return trivial_block(0);
+        return lin({{flag, v}}, 0, 1u | (1u << v));
+    }
+    return bivar(blk, flag, [](int x, int c) { return (c & 1) ? x : 0; });
+}
+
+Char Graph::mul_flag_char(BlockId flag, const Char& c) {
+    return Char{mul_flag(flag, c[0]), mul_flag(flag, c[1]), mul_flag(flag, c[2]), mul_flag(flag, c[3])};
+}
+
+Char Graph::add_disjoint(const std::vector<Char>& parts) {
+    Char r;
+    for (int b = 0; b < 4; b++) {
+        std::vector<std::pair<BlockId, int>> ops;
+        uint32_t vs = 1;
+        for (auto& p : parts) { ops.push_back({p[b], 1}); vs |= nodes[p[b]].vset & 0xF; }
+        r[b] = lin(ops, 0, vs);
+    }
+    return r;
+}
+
+// Stable compaction.  z_i = number of NUL chars before position i; a non-NUL char has to move left by z_i.
+// Routing by the bits of z_i, least significant first, never makes two chars meet (for p < q non-NUL,
+// z_q - z_p <= q - p - 1, and the partial shifts differ by at most that).  Every position carries its char
+// blocks plus z as base-4 control digits (two routing bits per block, forced to 0 on NUL chars so that they
+// "stay" and contribute nothing); layer b rebuilds position i as
+//     stay(x_i, ctrl_i) + move(x_{i+2^b}, ctrl_{i+2^b})
+// with two bivariate LUTs per carried block.  z_i comes from chunked prefix counts: an exact base count per
+// chunk of 13 (sum_digits over the flag prefix, shared through CSE) plus the local count (<= 12, leveled),
+// normalised by one carry chain.
+std::vector<Char> Graph::compact_nonzero(const std::vector<Char>& s) {
+    const size_t L = s.size();
+    if (L <= 1) return s;
+    int B = 0;
+    while ((1u << B) < L) B++;  // shifts are < L <= 2^B
+    const int nd = (B + 1) / 2;
+    std::vector<BlockId> nzb(L), zf(L);
+    for (size_t i = 0; i < L; i++) { nzb[i] = cond_bit(s[i]); zf[i] = not_flag(nzb[i]); }
+    const size_t m = 13;
+    std::vector<std::vector<BlockId>> ctrl(L, std::vector<BlockId>(nd));
+    auto msg_tab = table_of([](int v) { return v & 3; });
+    auto car_tab = table_of([](int v) { return v >> 2; });
+    for (size_t c0 = 0; c0 < L; c0 += m) {
+        std::vector<BlockId> base = sum_digits(std::vector<BlockId>(zf.begin(), zf.begin() + c0), nd);
+        for (size_t i = c0; i < std::min(L, c0 + m); i++) {
+            std::vector<std::pair<BlockId, int>> loc;
+            for (size_t k = c0; k < i; k++) loc.push_back({zf[k], 1});
+            BlockId carry = lin(loc, 0);
+            for (int d = 0; d < nd; d++) {
+                const BlockId cur = lin({{base[d], 1}, {carry, 1}}, 0);
+                BlockId digit;
+                if (!(nodes[cur].vset & ~0xFu)) { digit = cur; carry = trivial_block(0); }
+                else {
+                    digit = pbs({{cur, 1}}, 0, msg_tab);
+                    carry = d + 1 < nd ? pbs({{cur, 1}}, 0, car_tab) : trivial_block(0);
+                }
+                ctrl[i][d] = mul_flag(nzb[i], digit);
+            }
+        }
+    }
+    std::vector<Char> cur = s;
+    for (int b = 0; b < B; b++) {
+        const size_t sh = (size_t)1 << b;
+        const int kb = b / 2, bit = b & 1;
+        const int first_ctrl = bit ? kb + 1 : kb;  // control digits still needed after this layer
+        auto stay_f = [bit](int x, int y) { return ((y >> bit) & 1) ? 0 : x; };
+        auto move_f = [bit](int x, int y) { return ((y >> bit) & 1) ? x : 0; };
+        auto route = [&](BlockId x_here, BlockId y_here, BlockId x_in, BlockId y_in, bool has_in) {
+            BlockId st = (x_here == y_here) ? pbs({{x_here, 1}}, 0, table_of([&](int v) { return stay_f(v & 3, v & 3); }))
+                                            : bivar(x_here, y_here, stay_f);
+            if (!has_in) return st;
+            BlockId mv = (x_in == y_in) ? pbs({{x_in, 1}}, 0, table_of([&](int v) { return move_f(v & 3, v & 3); }))
+                                        : bivar(x_in, y_in, move_f);
+                    return lin({{st, 1}, {mv, 1}}, 0, 1u | ((nodes[x_here].vset | nodes[x_in].vset) & 0xF));
+        };
+        std::vector<Char> nxt(L);
+        std::vector<std::vector<BlockId>> nctrl(L, std::vector<BlockId>(nd));
+        for (size_t i = 0; i < L; i++) {
+            const bool has_in = i + sh < L;
+            const BlockId y_here = ctrl[i][kb];
+            const BlockId y_in = has_in ? ctrl[i + sh][kb] : trivial_block(0);
+            for (int q = 0; q < 4; q++) nxt[i][q] = route(cur[i][q], y_here, has_in ? cur[i + sh][q] : trivial_block(0), y_in, has_in);
+            for (int d = 0; d < nd; d++)
+                nctrl[i][d] = d >= first_ctrl ? route(ctrl[i][d], y_here, has_in ? ctrl[i + sh][d] : trivial_block(0), y_in, has_in)
+                                              : trivial_block(0);
+        }
+        cur.swap(nxt);
+        ctrl.swap(nctrl);
+    }
+    return cur;
+}
 
 Char Graph::nonzero(const Char& a) { return flag_char(cond_bit(a)); }
 
@@ -501,10 +603,14 @@ Char Graph::select_by_one_hot(const std::vector<Char>& onehot, const std::vector
 }
 
 // ------------------------------------------------------------------------------------ compile
-bool Graph::compile(CompiledProgram& out, std::string& err) {
+// Incremental: every call emits the jobs of the nodes that are reachable from the outputs marked since
+// the last commit() and have not been computed yet.  After the program has run, commit() turns everything
+// that now has an arena slot into level-0 atoms, so recording can simply continue (the eager path of the
+// reference's one-op-at-a-time callers is "record one op, compile, run, commit").
+bool Graph::compile(CompiledProgram& out, std::string& err, uint32_t slot_align) {
     if (!error.empty()) { err = error; return false; }
+    if (slot_align == 0) slot_align = 1;
     out = CompiledProgram();
-    // reachability from the outputs
     std::vector<char> live(nodes.size(), 0);
     std::vector<BlockId> stack;
     for (auto b : outputs) {
@@ -514,32 +620,32 @@ bool Graph::compile(CompiledProgram& out, std::string& err) {
     while (!stack.empty()) {
         const BlockId b = stack.back();
         stack.pop_back();
+        if (nodes[b].done) continue;
         for (auto& t : nodes[b].terms)
             if (!live[t.blk]) { live[t.blk] = 1; stack.push_back(t.blk); }
     }
-    // inputs keep their creation order in slots [0, n_inputs) whether live or not (callers upload by index)
-    uint32_t slot = 0;
-    for (size_t b = 0; b < nodes.size(); b++)
-        if (nodes[b].kind == BKind::Input) nodes[b].slot = (int32_t)slot++;
-    out.n_inputs = slot;
     for (auto b : outputs)
         if (nodes[b].kind == BKind::Trivial && nodes[b].slot < 0) {
-            nodes[b].slot = (int32_t)slot++;
+            nodes[b].slot = (int32_t)next_slot++;
             out.trivial_slots.push_back({(uint32_t)nodes[b].slot, (uint8_t)nodes[b].cst});
         }
     int depth = 0;
-    for (size_t b = 0; b < nodes.size(); b++) if (live[b]) depth = std::max(depth, (int)nodes[b].level);
+    for (size_t b = 0; b < nodes.size(); b++) if (live[b] && !nodes[b].done) depth = std::max(depth, (int)nodes[b].level);
     std::vector<std::vector<BlockId>> pbs_at(depth + 1), lin_at(depth + 1);
     for (size_t b = 0; b < nodes.size(); b++) {
-        if (!live[b]) continue;
+        if (!live[b] || nodes[b].done) continue;
         if (nodes[b].kind == BKind::Pbs) pbs_at[nodes[b].level].push_back((BlockId)b);
         else if (nodes[b].kind == BKind::Linear && nodes[b].materialized) lin_at[nodes[b].level].push_back((BlockId)b);
     }
     for (int l = 0; l <= depth; l++) {
-        for (auto b : pbs_at[l]) nodes[b].slot = (int32_t)slot++;
-        for (auto b : lin_at[l]) nodes[b].slot = (int32_t)slot++;
+        // the PBS results of a level are contiguous and padded to a multiple of slot_align, so that with
+        // `slot_align` ranks every rank's share is one equal slice of one all-gather buffer
+        for (auto b : pbs_at[l]) nodes[b].slot = (int32_t)next_slot++;
+        if (!pbs_at[l].empty()) next_slot += (slot_align - pbs_at[l].size() % slot_align) % slot_align;
+        for (auto b : lin_at[l]) nodes[b].slot = (int32_t)next_slot++;
     }
-    out.n_slots = slot;
+    out.n_slots = next_slot;
+    out.n_inputs = n_input_nodes;
     auto emit = [&](BlockId b) {
         const BlockNode& n = nodes[b];
         fhestr_job j;
@@ -567,7 +673,23 @@ bool Graph::compile(CompiledProgram& out, std::string& err) {
         out.n_pbs += pbs_at[l].size();
         out.level_offsets.push_back((uint32_t)out.jobs.size());
     }
+    pending.clear();
+    for (size_t b = 0; b < nodes.size(); b++)
+        if (live[b] && !nodes[b].done && nodes[b].slot >= 0) pending.push_back((BlockId)b);
     return true;
+}
+
+void Graph::commit() {
+    for (auto b : pending) { nodes[b].done = true; nodes[b].level = 0; }
+    pending.clear();
+    outputs.clear();
+    // values that exist are level-0 atoms now; re-level whatever has been recorded but not computed
+    for (size_t b = 0; b < nodes.size(); b++) {
+        BlockNode& n = nodes[b];
+        if (n.done || n.terms.empty()) continue;
+        if (n.kind == BKind::Pbs) n.level = 1 + level_of(n.terms, false);
+        else if (n.kind == BKind::Linear) n.level = level_of(n.terms, true);
+    }
 }
 
 }  // namespace fhestr

@@ -48,7 +48,8 @@ struct BlockNode {
     int32_t lut = -1;            // Pbs: graph-local LUT id
     std::vector<Term> terms;     // Pbs input / Linear definition, over atoms only
     int32_t cst = 0;             // constant in units of delta (mod 32)
-    int32_t slot = -1;           // arena slot, assigned by compile()
+    int32_t slot = -1;           // arena slot, assigned by compile() (inputs: at creation)
+    bool done = false;           // value exists in the arena (input, or computed and committed)
 };
 
 struct CompiledProgram {
@@ -102,6 +103,17 @@ public:
     Char sum_flags(const std::vector<Char>& flags);   // u8 sum (mod 256) of 0/1 chars
     Char nonzero(const Char& a);                      // a != 0 as one PBS over the block sum
     Char block_and_eq(const std::vector<std::pair<Char, Char>>& pairs);  // AND_i (a_i == b_i), block level
+    // generalisation of sum_flags: exact sum of 0/1 blocks as `ndigits` clean base-4 digits (little endian)
+    std::vector<BlockId> sum_digits(const std::vector<BlockId>& flags, int ndigits);
+    BlockId cond_bit(const Char& c);                  // c != 0 as a 0/1 block (scalar_ne(c, 0))
+    Char flag_char(BlockId b);                        // BooleanBlock::into_radix: [b, 0, 0, 0]
+    BlockId not_flag(BlockId b);                      // 1 - b, leveled
+    BlockId mul_flag(BlockId flag, BlockId blk);      // flag ? blk : 0 for a clean 2-bit blk
+    Char mul_flag_char(BlockId flag, const Char& c);
+    Char add_disjoint(const std::vector<Char>& parts); // block-wise sum of chars of which at most one is non-zero
+    // stable compaction: non-NUL chars first, order kept (== bubble_zeroes_right in value), as a
+    // log-depth routing network driven by the per-char count of preceding NULs
+    std::vector<Char> compact_nonzero(const std::vector<Char>& s);
     // one-hot of the first set flag (all zero if none) -- replaces priority-select chains
     std::vector<Char> first_one_hot(const std::vector<Char>& flags, Char* any);
     // u8 value sum_i onehot_i * value_i + (none ? none_value : 0), refreshed to clean blocks
@@ -110,7 +122,10 @@ public:
     // ---- compile
     void mark_output(const Char& c) { for (auto b : c) outputs.push_back(b); }
     // returns false and fills error on failure
-    bool compile(CompiledProgram& out, std::string& error);
+    bool compile(CompiledProgram& out, std::string& error, uint32_t slot_align = 1);
+    void commit();               // the compiled program has run: its results are level-0 atoms from now on
+    uint32_t slots_used() const { return next_slot; }
+    void reserve_slots(uint32_t first_free) { if (first_free > next_slot) next_slot = first_free; }
     int slot_of(BlockId b) const { return nodes[b].slot; }
     const std::vector<std::array<uint8_t, 16>>& luts() const { return lut_tables; }
     uint64_t pbs_recorded() const { return n_pbs_nodes; }
@@ -126,6 +141,9 @@ private:
     BlockId triv_cache[32];
     bool triv_cache_init = false;
     uint64_t n_pbs_nodes = 0;
+    uint32_t next_slot = 0;
+    uint32_t n_input_nodes = 0;
+    std::vector<BlockId> pending;  // nodes given a slot by the last compile()
 
     int lut_id(const std::array<uint8_t, 16>& t);
     void flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, std::vector<Term>& terms, int& out_cst);
@@ -135,9 +153,7 @@ private:
     bool signed_ok = false;
     void fail(const std::string& m) { if (error.empty()) error = m; }
     Char cmp(const Char& a, const Char& b, int op);
-    Char flag_char(BlockId b);
     std::array<BlockId, 4> propagate(std::array<BlockId, 4> s);
-    BlockId cond_bit(const Char& c);
 };
 
 }  // namespace fhestr

@@ -1,0 +1,606 @@
+// strings.cpp -- see strings.h.  Each method names the reference function it restates; the faithful
+// branch issues the reference's own primitive sequence, the fast branch a plaintext-identical rewrite.
+#include "strings.h"
+
+#include <algorithm>
+
+namespace fhestr {
+
+static const size_t kMaxFindLength = 255;   // /root/reference/src/main.rs:20
+static const size_t kMaxRepetitions = 16;   // /root/reference/src/main.rs:17
+
+static size_t adjust_end_of_pattern(size_t e) { return e == 0 ? 1 : e; }  // utils.rs:106
+
+// ------------------------------------------------------------------------------------ helpers
+Char StringOps::match_at(const Str& s, size_t i, const Str& pattern, bool reversed) {
+    if (fast) {
+        std::vector<std::pair<Char, Char>> pairs;
+        for (size_t j = 0; j < pattern.size(); j++) pairs.push_back({pattern[j], s[i + j]});
+        return g.block_and_eq(pairs);
+    }
+    Char flag = one();
+    for (size_t jj = 0; jj < pattern.size(); jj++) {
+        const size_t j = reversed ? pattern.size() - 1 - jj : jj;
+        flag = g.bitand_(flag, g.eq(pattern[j], s[i + j]));
+    }
+    return flag;
+}
+
+Char StringOps::char_cmp(const Char& a, const Char& b, int op) {
+    switch (op) {
+        case 0: return g.lt(a, b);
+        case 1: return g.le(a, b);
+        case 2: return g.gt(a, b);
+        default: return g.ge(a, b);
+    }
+}
+
+std::vector<Char> StringOps::last_one_hot(const std::vector<Char>& flags, Char* any) {
+    std::vector<Char> rev(flags.rbegin(), flags.rend());
+    std::vector<Char> r = g.first_one_hot(rev, any);
+    std::reverse(r.begin(), r.end());
+    return r;
+}
+
+// 1 unless c is NUL or ASCII whitespace (0x09-0x0D, 0x20): two nibble classifiers and one combiner
+Char StringOps::is_not_blank(const Char& c) {
+    std::array<uint8_t, 16> th{}, tl{}, tc{};
+    for (int v = 0; v < 16; v++) {
+        th[v] = v == 0 ? 1 : (v == 2 ? 2 : 0);
+        tl[v] = v == 0 ? 1 : ((v >= 9 && v <= 13) ? 2 : 0);
+    }
+    for (int v = 0; v < 16; v++) {
+        const int h = v >> 2, l = v & 3;
+        const bool blank = (h == 1 && l >= 1) || (h == 2 && l == 1);
+        tc[v] = blank ? 0 : 1;
+    }
+    const BlockId h = g.pbs({{c[3], 4}, {c[2], 1}}, 0, th);
+    const BlockId l = g.pbs({{c[1], 4}, {c[0], 1}}, 0, tl);
+    return g.flag_char(g.pbs({{h, 4}, {l, 1}}, 0, tc));
+}
+
+// flag: c in [first, first + 25] for first = 0x41 ('A'..'Z') or 0x61 ('a'..'z')
+static Char letter_range_flag(Graph& g, const Char& c, int first) {
+    const int row = first >> 4;
+    std::array<uint8_t, 16> th{}, tl{}, tc{};
+    for (int v = 0; v < 16; v++) {
+        th[v] = v == row ? 1 : (v == row + 1 ? 2 : 0);
+        tl[v] = v == 0 ? 0 : (v <= 10 ? 1 : 2);
+    }
+    for (int v = 0; v < 16; v++) {
+        const int h = v >> 2, l = v & 3;
+        tc[v] = ((h == 1 && l >= 1) || (h == 2 && l <= 1)) ? 1 : 0;
+    }
+    const BlockId h = g.pbs({{c[3], 4}, {c[2], 1}}, 0, th);
+    const BlockId l = g.pbs({{c[1], 4}, {c[0], 1}}, 0, tl);
+    return g.flag_char(g.pbs({{h, 4}, {l, 1}}, 0, tc));
+}
+
+// suffix OR of 0/1 blocks: out[i] = OR_{k >= i} f[k]; chunks of 15, chunk ORs scanned recursively
+static std::vector<BlockId> suffix_or(Graph& g, const std::vector<BlockId>& f) {
+    const size_t n = f.size(), m = 14;
+    std::array<uint8_t, 16> nz{};
+    for (int v = 1; v < 16; v++) nz[v] = 1;
+    std::vector<BlockId> out(n);
+    if (n == 0) return out;
+    std::vector<BlockId> chunk_or;
+    for (size_t c0 = 0; c0 < n; c0 += m) {
+        std::vector<std::pair<BlockId, int>> ops;
+        for (size_t k = c0; k < std::min(n, c0 + m); k++) ops.push_back({f[k], 1});
+        chunk_or.push_back(ops.size() == 1 ? ops[0].first : g.pbs(ops, 0, nz));
+    }
+    std::vector<BlockId> later;  // later[c] = OR of chunks > c
+    if (chunk_or.size() > 1) {
+        std::vector<BlockId> tail(chunk_or.begin() + 1, chunk_or.end());
+        later = suffix_or(g, tail);
+    }
+    for (size_t c0 = 0, c = 0; c0 < n; c0 += m, c++) {
+        const size_t hi = std::min(n, c0 + m);
+        for (size_t i = c0; i < hi; i++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t k = i; k < hi; k++) ops.push_back({f[k], 1});
+            if (c < later.size()) ops.push_back({later[c], 1});
+            out[i] = ops.size() == 1 ? ops[0].first : g.pbs(ops, 0, nz);
+        }
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------ utils.rs
+Str StringOps::bubble_zeroes_right(const Str& s) {
+    if (fast) return g.compact_nonzero(s);
+    Str r = s;
+    const size_t n = r.size();
+    for (size_t pass = 0; pass < n; pass++)
+        for (size_t i = 0; i + 1 < n; i++) {
+            const Char should_swap = g.eq(r[i], zero());
+            const Char a = g.if_then_else(should_swap, r[i + 1], r[i]);
+            const Char b = g.if_then_else(should_swap, zero(), r[i + 1]);
+            r[i] = a;
+            r[i + 1] = b;
+        }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------ mod.rs
+Str StringOps::to_upper(const Str& s) {
+    Str out;
+    const Char cst = g.trivial_char(32);  // fhestring.rs:24
+    for (auto& b : s) {
+        if (fast) {
+            const BlockId f = letter_range_flag(g, b, 0x61)[0];
+            Char r = b;
+            r[2] = g.lin({{b[2], 1}, {f, -2}}, 0, 0xF);
+            out.push_back(r);
+        } else {
+            const Char not_lower = g.flip(g.is_lowercase(b));
+            out.push_back(g.sub(b, g.if_then_else(not_lower, zero(), cst)));
+        }
+    }
+    return out;
+}
+
+Str StringOps::to_lower(const Str& s) {
+    Str out;
+    const Char cst = g.trivial_char(32);
+    for (auto& b : s) {
+        if (fast) {
+            const BlockId f = letter_range_flag(g, b, 0x41)[0];
+            Char r = b;
+            r[2] = g.lin({{b[2], 1}, {f, 2}}, 0, 0xF);
+            out.push_back(r);
+        } else {
+            const Char not_upper = g.flip(g.is_uppercase(b));
+            out.push_back(g.add(b, g.if_then_else(not_upper, zero(), cst)));
+        }
+    }
+    return out;
+}
+
+Char StringOps::contains(const Str& s, const Str& needle) {
+    if (s.empty() && needle.empty()) return one();
+    if (needle.size() > s.size()) return zero();
+    const size_t end = s.size() - needle.size();
+    if (fast) {
+        std::vector<Char> windows;
+        for (size_t i = 0; i <= end; i++) windows.push_back(match_at(s, i, needle, false));
+        return g.or_all(windows);
+    }
+    Char result = zero();
+    for (size_t i = 0; i <= end; i++) {
+        Char cur = one();
+        for (size_t j = 0; j < needle.size(); j++) cur = g.bitand_(cur, g.eq(s[i + j], needle[j]));
+        result = g.bitor_(result, cur);
+    }
+    return result;
+}
+
+Char StringOps::ends_with(const Str& s, const Str& needle) {
+    if (s.empty() && needle.empty()) return one();
+    if (needle.size() > s.size()) return zero();
+    const size_t end = s.size() - needle.size();
+    if (fast) {
+        // the last window made only of non-NUL chars decides
+        std::vector<Char> all_nonzero, match;
+        for (size_t i = 0; i <= end; i++) {
+            std::vector<Char> nz;
+            for (size_t j = 0; j < needle.size(); j++) nz.push_back(g.nonzero(s[i + j]));
+            all_nonzero.push_back(g.and_all(nz));
+            match.push_back(match_at(s, i, needle, false));
+        }
+        const std::vector<Char> last = last_one_hot(all_nonzero, nullptr);
+        std::vector<Char> terms;
+        for (size_t i = 0; i <= end; i++) terms.push_back(g.flag_char(g.mul_flag(last[i][0], match[i][0])));
+        return g.or_all(terms);
+    }
+    Char result = zero();
+    for (size_t i = 0; i <= end; i++) {
+        Char cur = one(), nonzero = one();
+        for (size_t j = 0; j < needle.size(); j++) {
+            cur = g.bitand_(cur, g.eq(s[i + j], needle[j]));
+            nonzero = g.bitand_(nonzero, g.ne(s[i + j], zero()));
+        }
+        result = g.if_then_else(nonzero, cur, result);
+    }
+    return result;
+}
+
+Char StringOps::starts_with(const Str& s, const Str& pattern) {
+    if (pattern.size() > s.size()) return zero();
+    if (s.empty() && pattern.empty()) return one();
+    if (fast) return match_at(s, 0, pattern, false);
+    Char result = one();
+    for (size_t j = 0; j < pattern.size(); j++) result = g.bitand_(result, g.eq(s[j], pattern[j]));
+    return result;
+}
+
+Char StringOps::is_empty(const Str& s) {
+    if (s.empty()) return one();
+    if (fast) {
+        std::vector<Char> nz;
+        for (auto& c : s) nz.push_back(g.nonzero(c));
+        return g.flag_char(g.not_flag(g.or_all(nz)[0]));
+    }
+    Char result = one();
+    for (auto& c : s) result = g.bitand_(result, g.eq(c, zero()));
+    return result;
+}
+
+Char StringOps::len(const Str& s) {
+    if (s.empty()) return zero();
+    if (fast) {
+        std::vector<Char> nz;
+        for (auto& c : s) nz.push_back(g.nonzero(c));
+        return g.sum_flags(nz);
+    }
+    Char result = zero();
+    for (auto& c : s) result = g.add(result, g.ne(c, zero()));
+    return result;
+}
+
+Str StringOps::repeat_clear(const Str& s, size_t repetitions) {
+    if (repetitions == 0) return Str();
+    Str r;
+    for (size_t k = 0; k < repetitions; k++) r.insert(r.end(), s.begin(), s.end());
+    return bubble_zeroes_right(r);
+}
+
+Str StringOps::repeat(const Str& s, const Char& repetitions) {
+    const size_t n = s.size();
+    Str r(kMaxRepetitions * n, zero());
+    for (size_t i = 0; i < kMaxRepetitions; i++) {
+        const Char copy_flag = g.lt(g.trivial_char((uint8_t)i), repetitions);
+        for (size_t j = 0; j < n; j++)
+            r[i * n + j] = fast ? g.mul_flag_char(copy_flag[0], s[j]) : g.if_then_else(copy_flag, s[j], zero());
+    }
+    return bubble_zeroes_right(r);
+}
+
+Str StringOps::handle_longer_from(const Str& bytes_in, const Str& from, Str to, const Char& n, bool use_counter) {
+    Str bytes = bytes_in;
+    bytes.push_back(zero());
+    while (to.size() < from.size()) to.push_back(zero());
+    Str result = bytes;
+    if (from.size() > result.size()) return bubble_zeroes_right(result);
+    const size_t end = adjust_end_of_pattern(result.size() - from.size());
+    if (!fast) {
+        Char counter = zero();
+        for (size_t i = 0; i < end; i++) {
+            Char flag = one();
+            for (size_t j = 0; j < from.size(); j++) flag = g.bitand_(flag, g.eq(from[j], bytes[i + j]));
+            if (use_counter) {
+                counter = g.add(counter, flag);
+                flag = g.bitand_(flag, g.ge(n, counter));
+            }
+            for (size_t k = 0; k < to.size(); k++) result[i + k] = g.if_then_else(flag, to[k], result[i + k]);
+        }
+        return bubble_zeroes_right(result);
+    }
+    // all match flags come from the ORIGINAL bytes (mod.rs:864), so they are independent
+    std::vector<Char> m(end);
+    for (size_t i = 0; i < end; i++) m[i] = match_at(bytes, i, from, false);
+    if (use_counter) {
+        // counter after window i = (number of RAW matches in windows 0..i) mod 256; prefix sums share
+        // their leading chunks through CSE
+        const std::vector<Char> raw = m;
+        for (size_t i = 0; i < end; i++) {
+            const Char counter = g.sum_flags(std::vector<Char>(raw.begin(), raw.begin() + i + 1));
+            m[i] = g.flag_char(g.mul_flag(g.ge(n, counter)[0], raw[i][0]));
+        }
+    }
+    const size_t T = to.size();
+    for (size_t p = 0; p < result.size(); p++) {
+        // windows i = p, p-1, ..., p-T+1 write position p; the largest i (written last) wins
+        std::vector<Char> cand;
+        std::vector<size_t> kk;
+        for (size_t k = 0; k < T && k <= p; k++) {
+            const size_t i = p - k;
+            if (i >= end) continue;
+            cand.push_back(m[i]);
+            kk.push_back(k);
+        }
+        if (cand.empty()) continue;
+        const std::vector<Char> first = g.first_one_hot(cand, nullptr);
+        std::vector<Char> parts;
+        std::vector<std::pair<BlockId, int>> none_ops;
+        for (size_t c = 0; c < cand.size(); c++) {
+            parts.push_back(g.mul_flag_char(first[c][0], to[kk[c]]));
+            none_ops.push_back({first[c][0], -1});
+        }
+        const BlockId none = g.lin(none_ops, 1, 0x3);
+        parts.push_back(g.mul_flag_char(none, bytes[p]));
+        result[p] = g.add_disjoint(parts);
+    }
+    return bubble_zeroes_right(result);
+}
+
+Str StringOps::handle_shorter_from(const Str& bytes_in, const Str& from, const Str& to, const Char& n, bool use_counter) {
+    // op-by-op in both modes (the copy-buffer scheme is inherently serial in i)
+    Str bytes = bytes_in;
+    bytes.push_back(zero());
+    const size_t size_difference = to.size() - from.size();
+    size_t max_len = bytes.empty() ? to.size() : to.size() * bytes.size() + bytes.size();
+    if (from.empty()) max_len = (bytes.size() + (bytes.size() + 1) * to.size()) + 1;
+    Str result = bytes;
+    while (result.size() < max_len) result.push_back(zero());
+    Str copy_buffer(max_len, zero());
+    Str ignore(max_len, one());
+    Char counter = zero();
+    for (size_t i = 0; i + to.size() < result.size(); i++) {
+        Char flag = one();
+        for (size_t j = 0; j < from.size(); j++) {
+            flag = g.bitand_(flag, g.eq(from[j], result[i + j]));
+            flag = g.bitand_(flag, ignore[i + j]);
+        }
+        if (from.empty()) flag = (i % (to.size() + 1) == 0) ? one() : zero();
+        if (use_counter) {
+            counter = g.add(counter, flag);
+            flag = g.bitand_(flag, g.ge(n, counter));
+        }
+        for (size_t k = 0; k < max_len; k++) copy_buffer[k] = g.if_then_else(flag, result[k], zero());
+        for (size_t k = 0; k < to.size(); k++) {
+            result[i + k] = g.if_then_else(flag, to[k], result[i + k]);
+            ignore[i + k] = g.bitand_(ignore[i + k], g.if_then_else(flag, zero(), one()));
+        }
+        for (size_t k = i + to.size(); k < max_len; k++)
+            result[k] = g.if_then_else(flag, copy_buffer[k - size_difference], result[k]);
+    }
+    return result;
+}
+
+Str StringOps::replace(const Str& s, const Str& from, const Str& to) {
+    if (from.size() >= to.size()) return handle_longer_from(s, from, to, zero(), false);
+    return handle_shorter_from(s, from, to, zero(), false);
+}
+
+Str StringOps::replacen(const Str& s, const Str& from, const Str& to, const Char& n) {
+    if (from.size() >= to.size()) return handle_longer_from(s, from, to, n, true);
+    return handle_shorter_from(s, from, to, n, true);
+}
+
+bool StringOps::rfind(const Str& s_in, const Str& pattern, Char& out) {
+    Str s = s_in;
+    s.push_back(zero());
+    if (s.size() >= kMaxFindLength + pattern.size()) {
+        error = "Maximum supported size for find reached";
+        return false;
+    }
+    if (pattern.empty()) {
+        if (fast) {
+            std::vector<Char> nz;
+            std::vector<uint8_t> values;
+            for (size_t i = 0; i < s.size(); i++) { nz.push_back(g.nonzero(s[i])); values.push_back((uint8_t)(i + 1)); }
+            out = g.select_by_one_hot(last_one_hot(nz, nullptr), values, zero(), 0);
+            return true;
+        }
+        Char last = zero();
+        for (size_t i = 0; i < s.size(); i++)
+            last = g.if_then_else(g.ne(s[i], zero()), g.trivial_char((uint8_t)(i + 1)), last);
+        out = last;
+        return true;
+    }
+    if (pattern.size() > s.size()) { out = g.trivial_char(255); return true; }
+    const size_t end = adjust_end_of_pattern(s.size() - pattern.size());
+    if (fast) {
+        std::vector<Char> m;
+        std::vector<uint8_t> values;
+        for (size_t i = 0; i < end; i++) { m.push_back(match_at(s, i, pattern, false)); values.push_back((uint8_t)i); }
+        Char any;
+        const std::vector<Char> last = last_one_hot(m, &any);
+        out = g.select_by_one_hot(last, values, g.flag_char(g.not_flag(any[0])), (uint8_t)kMaxFindLength);
+        return true;
+    }
+    Char pos = g.trivial_char((uint8_t)kMaxFindLength);
+    for (size_t i = 0; i < end; i++)
+        pos = g.if_then_else(match_at(s, i, pattern, false), g.trivial_char((uint8_t)i), pos);
+    out = pos;
+    return true;
+}
+
+bool StringOps::find(const Str& s, const Str& pattern, Char& out) {
+    if (s.empty() && pattern.empty()) { out = zero(); return true; }
+    if (s.size() >= kMaxFindLength + pattern.size()) {
+        error = "Maximum supported size for find reached";
+        return false;
+    }
+    if (pattern.size() > s.size()) { out = g.trivial_char(255); return true; }
+    const size_t end = s.size() - pattern.size();
+    if (fast) {
+        std::vector<Char> m;
+        std::vector<uint8_t> values;
+        for (size_t i = 0; i <= end; i++) { m.push_back(match_at(s, i, pattern, true)); values.push_back((uint8_t)i); }
+        Char any;
+        const std::vector<Char> first = g.first_one_hot(m, &any);
+        out = g.select_by_one_hot(first, values, g.flag_char(g.not_flag(any[0])), (uint8_t)kMaxFindLength);
+        return true;
+    }
+    Char pos = g.trivial_char((uint8_t)kMaxFindLength);
+    for (size_t ii = 0; ii <= end; ii++) {
+        const size_t i = end - ii;
+        pos = g.if_then_else(match_at(s, i, pattern, true), g.trivial_char((uint8_t)i), pos);
+    }
+    out = pos;
+    return true;
+}
+
+Char StringOps::eq(const Str& s, const Str& o) {
+    const size_t n = std::min(s.size(), o.size());
+    const Char len1 = len(s), len2 = len(o);
+    if (fast) {
+        // (s_i == 0 && o_i == 0) || s_i == o_i  is just s_i == o_i; the length test joins the same AND
+        std::vector<std::pair<Char, Char>> pairs;
+        for (size_t i = 0; i < n; i++) pairs.push_back({s[i], o[i]});
+        pairs.push_back({len1, len2});
+        return g.block_and_eq(pairs);
+    }
+    Char is_eq = one();
+    const Char lengths_ne = g.ne(len1, len2);
+    for (size_t i = 0; i < n; i++) {
+        const Char are_equal = g.eq(s[i], o[i]);
+        Char res = g.bitand_(g.eq(s[i], zero()), g.eq(o[i], zero()));
+        res = g.bitor_(res, are_equal);
+        is_eq = g.bitand_(is_eq, res);
+    }
+    return g.if_then_else(lengths_ne, zero(), is_eq);
+}
+
+Char StringOps::ne(const Str& s, const Str& o) {
+    const Char e = eq(s, o);
+    return fast ? g.flag_char(g.not_flag(e[0])) : g.flip(e);
+}
+
+Char StringOps::eq_ignore_case(const Str& s, const Str& o) { return eq(to_lower(s), to_lower(o)); }
+
+StripResult StringOps::strip_prefix(const Str& s, const Str& pattern) {
+    Str result = s;
+    if (pattern.size() > result.size()) return StripResult{result, zero()};
+    const size_t end = std::min(pattern.size(), result.size());
+    Char flag = one();
+    if (end == 0 && !pattern.empty() && s.empty()) flag = zero();
+    if (fast) {
+        if (end > 0) flag = match_at(result, 0, pattern, false);
+        const BlockId keep = g.not_flag(flag[0]);
+        for (size_t j = 0; j < end; j++) result[j] = g.mul_flag_char(keep, result[j]);
+    } else {
+        for (size_t j = 0; j < end; j++) flag = g.bitand_(flag, g.eq(pattern[j], result[j]));
+        for (size_t j = 0; j < end; j++) result[j] = g.if_then_else(flag, zero(), result[j]);
+    }
+    return StripResult{bubble_zeroes_right(result), flag};
+}
+
+StripResult StringOps::strip_suffix(const Str& s_in, const Str& needle) {
+    Str s = s_in;
+    if (needle.size() > s.size()) return StripResult{s, zero()};
+    const size_t end = s.size() - needle.size();
+    if (fast && s.size() <= 255) {
+        std::vector<Char> all_nonzero, match;
+        for (size_t i = 0; i <= end; i++) {
+            std::vector<Char> nz;
+            for (size_t j = 0; j < needle.size(); j++) nz.push_back(g.nonzero(s[i + j]));
+            all_nonzero.push_back(g.and_all(nz));
+            match.push_back(match_at(s, i, needle, false));
+        }
+        const std::vector<Char> last = last_one_hot(all_nonzero, nullptr);
+        std::vector<BlockId> sel(end + 1);
+        std::vector<Char> sel_c;
+        for (size_t i = 0; i <= end; i++) { sel[i] = g.mul_flag(last[i][0], match[i][0]); sel_c.push_back(g.flag_char(sel[i])); }
+        const Char should = g.or_all(sel_c);
+        for (size_t p = 0; p < s.size(); p++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t j = 0; j < needle.size() && j <= p; j++)
+                if (p - j <= end) ops.push_back({sel[p - j], -1});
+            if (ops.empty()) continue;
+            s[p] = g.mul_flag_char(g.lin(ops, 1, 0x3), s[p]);
+        }
+        return StripResult{s, should};
+    }
+    const Char two_five_five = g.trivial_char(255);
+    Char pos = two_five_five;
+    for (size_t i = 0; i <= end; i++) {
+        Char found = one(), nonzero = one();
+        for (size_t j = 0; j < needle.size(); j++) {
+            found = g.bitand_(found, g.eq(s[i + j], needle[j]));
+            nonzero = g.bitand_(nonzero, g.ne(s[i + j], zero()));
+        }
+        const Char cur = g.if_then_else(found, g.trivial_char((uint8_t)i), two_five_five);
+        pos = g.if_then_else(nonzero, cur, pos);
+    }
+    const Char should = g.ne(pos, two_five_five);
+    for (size_t i = 0; i <= end; i++) {
+        const Char mask = g.eq(g.trivial_char((uint8_t)i), pos);
+        for (size_t j = 0; j < needle.size(); j++) s[i + j] = g.if_then_else(mask, zero(), s[i + j]);
+    }
+    return StripResult{s, should};
+}
+
+Char StringOps::comparison(const Str& s_in, const Str& o_in, int op) {
+    Str s = s_in, o = o_in;
+    size_t n = std::min(s.size(), o.size());
+    if (n == 0) { s.push_back(zero()); o.push_back(zero()); n = 1; }
+    const Char len1 = len(s), len2 = len(o);
+    if (fast) {
+        // ret = comparison at the first differing index; without one, the length comparison decides
+        std::vector<Char> differs, cmp;
+        for (size_t i = 0; i < n; i++) { differs.push_back(g.ne(s[i], o[i])); cmp.push_back(char_cmp(s[i], o[i], op)); }
+        Char any;
+        const std::vector<Char> first = g.first_one_hot(differs, &any);
+        std::vector<Char> terms;
+        for (size_t i = 0; i < n; i++) terms.push_back(g.flag_char(g.mul_flag(first[i][0], cmp[i][0])));
+        const Char at_first = g.or_all(terms);
+        const Char by_len = char_cmp(len1, len2, op);   // ge == (eq | gt), le == (eq | lt) on u8
+        std::array<uint8_t, 16> t{};
+        for (int v = 0; v < 16; v++) t[v] = (v & 2) ? (v & 1) : ((v >> 2) & 1);
+        return g.flag_char(g.pbs({{at_first[0], 1}, {any[0], 2}, {by_len[0], 4}}, 0, t));
+    }
+    Char encountered = zero(), became_one = zero(), ret = g.trivial_char(255);
+    for (size_t i = 0; i < n; i++) {
+        const Char cmp = char_cmp(s[i], o[i], op);
+        const Char is_ne = g.ne(s[i], o[i]);
+        encountered = g.bitor_(encountered, is_ne);
+        const Char flag = g.bitand_(encountered, g.flip(became_one));
+        became_one = g.bitor_(became_one, flag);
+        ret = g.if_then_else(flag, cmp, ret);
+    }
+    const Char substrings_equal = g.eq(ret, g.trivial_char(255));
+    const Char l_eq = g.eq(len1, len2), l_gt = g.gt(len1, len2), l_lt = g.lt(len1, len2);
+    Char length_based;
+    switch (op) {
+        case 3: length_based = g.bitor_(l_eq, l_gt); break;
+        case 1: length_based = g.bitor_(l_eq, l_lt); break;
+        case 2: length_based = l_gt; break;
+        default: length_based = l_lt; break;
+    }
+    return g.if_then_else(substrings_equal, length_based, ret);
+}
+
+Str StringOps::concatenate(const Str& s, const Str& o) {
+    Str r = s;
+    r.insert(r.end(), o.begin(), o.end());
+    return bubble_zeroes_right(r);
+}
+
+// ------------------------------------------------------------------------------------ trim.rs
+Str StringOps::trim_end(const Str& s) {
+    Str result(s.size(), zero());
+    if (fast) {
+        std::vector<BlockId> nb;
+        for (auto& c : s) nb.push_back(is_not_blank(c)[0]);
+        const std::vector<BlockId> stop = suffix_or(g, nb);
+        for (size_t i = 0; i < s.size(); i++) result[i] = g.mul_flag_char(stop[i], s[i]);
+        return result;
+    }
+    Char stop = zero();
+    for (size_t ii = 0; ii < s.size(); ii++) {
+        const size_t i = s.size() - 1 - ii;
+        const Char is_not_zero = g.ne(s[i], zero());
+        const Char is_not_ws = g.flip(g.is_whitespace(s[i]));
+        stop = g.bitor_(stop, g.bitand_(is_not_ws, is_not_zero));
+        result[i] = g.if_then_else(stop, s[i], zero());
+    }
+    return result;
+}
+
+Str StringOps::trim_start(const Str& s) {
+    Str result(s.size(), zero());
+    if (fast) {
+        std::vector<BlockId> nb;
+        for (auto& c : s) nb.push_back(is_not_blank(c)[0]);
+        std::reverse(nb.begin(), nb.end());
+        std::vector<BlockId> stop = suffix_or(g, nb);
+        std::reverse(stop.begin(), stop.end());
+        for (size_t i = 0; i < s.size(); i++) result[i] = g.mul_flag_char(stop[i], s[i]);
+        return bubble_zeroes_right(result);
+    }
+    Char stop = zero();
+    for (size_t i = 0; i < s.size(); i++) {
+        const Char is_not_zero = g.ne(s[i], zero());
+        const Char is_not_ws = g.flip(g.is_whitespace(s[i]));
+        stop = g.bitor_(stop, g.bitand_(is_not_ws, is_not_zero));
+        result[i] = g.if_then_else(stop, s[i], zero());
+    }
+    return bubble_zeroes_right(result);
+}
+
+Str StringOps::trim(const Str& s) { return trim_start(trim_end(s)); }
+
+}  // namespace fhestr

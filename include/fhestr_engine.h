@@ -101,12 +101,94 @@ int fhestr_pbs_batch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_jobs);
 typedef struct fhestr_program fhestr_program;
 int fhestr_program_create(fhestr_engine* e, const fhestr_job* jobs, const uint32_t* level_offsets,
                           uint32_t n_levels, fhestr_program** out);
-/* run levels [first_level, last_level) ; rank/world shard each level's jobs (multi-GPU: the caller
- * all-gathers the arena slices between levels; see fhestr_program_level_range) */
+/* run levels [first_level, last_level).  world > 1 (after fhestr_comm_init): each level's PBS jobs are
+ * sharded over the ranks (fhestr_shard_range), the result blocks are all-gathered in place over NCCL, and
+ * the leveled jobs run replicated -- every rank ends each level with the same arena. */
 int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level, uint32_t last_level,
                        uint32_t rank, uint32_t world);
 int fhestr_program_level_jobs(const fhestr_program* p, uint32_t level, uint32_t* n_jobs);
 void fhestr_program_destroy(fhestr_program* p);
+
+/* ---- op graph: the reference's per-char primitives and string methods, recorded then batched ---------- */
+/* How the unchanged sequential callers of /root/reference/src/server_key/*.rs become dependency-level
+ * batches: every FheAsciiChar the Rust side holds is a 32-bit char id into a graph; the primitives of
+ * /root/reference/src/ciphertext/fheasciichar.rs:17-168 RECORD instead of computing; decrypt (or any
+ * explicit flush) compiles what is reachable into levels of independent PBS jobs and runs them.  Eager use
+ * is "record one op, execute" -- same calls, no batching. */
+typedef struct fhestr_graph fhestr_graph;
+
+enum {  /* fhestr_graph_char_op: FheAsciiChar methods (fheasciichar.rs line) */
+    FHESTR_OP_EQ = 0 /* :35 */, FHESTR_OP_NE = 1 /* :40 */, FHESTR_OP_LE = 2 /* :45 */, FHESTR_OP_LT = 3 /* :50 */,
+    FHESTR_OP_GE = 4 /* :55 */, FHESTR_OP_GT = 5 /* :60 */, FHESTR_OP_BITAND = 6 /* :65 */, FHESTR_OP_BITOR = 7 /* :74 */,
+    FHESTR_OP_SUB = 8 /* :83 */, FHESTR_OP_ADD = 9 /* :87 */, FHESTR_OP_IF_THEN_ELSE = 10 /* :93 */,
+    FHESTR_OP_IS_WHITESPACE = 11 /* :106 */, FHESTR_OP_IS_UPPERCASE = 12 /* :132 */,
+    FHESTR_OP_IS_LOWERCASE = 13 /* :146 */, FHESTR_OP_FLIP = 14 /* :161 */
+};
+enum {  /* fhestr_graph_string_op: MyServerKey methods (server_key/mod.rs line unless noted) */
+    FHESTR_M_CONTAINS = 0 /* :151 */, FHESTR_M_ENDS_WITH = 1 /* :241 */, FHESTR_M_STARTS_WITH = 2 /* :344 */,
+    FHESTR_M_IS_EMPTY = 3 /* :431 */, FHESTR_M_LEN = 4 /* :478 */, FHESTR_M_REPEAT_CLEAR = 5 /* :517 */,
+    FHESTR_M_REPEAT = 6 /* :567 */, FHESTR_M_REPLACE = 7 /* :624 */, FHESTR_M_RFIND = 8 /* :727 */,
+    FHESTR_M_FIND = 9 /* :1010 */, FHESTR_M_EQ = 10 /* :1122 */, FHESTR_M_NE = 11 /* :1178 */,
+    FHESTR_M_EQ_IGNORE_CASE = 12 /* :1221 */, FHESTR_M_STRIP_PREFIX = 13 /* :1261 */,
+    FHESTR_M_STRIP_SUFFIX = 14 /* :1335 */, FHESTR_M_LT = 15 /* :1577 */, FHESTR_M_LE = 16 /* :1613 */,
+    FHESTR_M_GT = 17 /* :1649 */, FHESTR_M_GE = 18 /* :1685 */, FHESTR_M_REPLACEN = 19 /* :1729 */,
+    FHESTR_M_CONCATENATE = 20 /* :1864 */, FHESTR_M_TO_UPPER = 21 /* :65 */, FHESTR_M_TO_LOWER = 22 /* :110 */,
+    FHESTR_M_TRIM_END = 23 /* trim.rs:36 */, FHESTR_M_TRIM_START = 24 /* trim.rs:86 */, FHESTR_M_TRIM = 25 /* trim.rs:146 */,
+    FHESTR_M_BUBBLE_ZEROES_RIGHT = 26 /* utils.rs:28 */
+};
+
+typedef struct {            /* one string argument: char ids in order (FheString / Vec<FheAsciiChar>) */
+    const uint32_t* chars;
+    uint32_t len;
+} fhestr_str_arg;
+
+typedef struct {
+    uint32_t n_levels, n_jobs, n_luts, n_trivial;
+    uint32_t slots_used;    /* arena blocks the graph needs so far */
+    uint64_t n_pbs;         /* PBS jobs in this compile */
+    uint64_t n_pbs_recorded;/* PBS nodes recorded since the graph was created (before dead-code elimination) */
+} fhestr_graph_info;
+
+int fhestr_graph_create(int32_t delta_log, fhestr_graph** out);
+void fhestr_graph_destroy(fhestr_graph* g);
+const char* fhestr_graph_last_error(const fhestr_graph* g);
+/* FheAsciiChar::encrypt (fheasciichar.rs:27): `count` encrypted chars; slots[4*i + b] is the arena block the
+ * caller must upload block b of char i to (fhestr_ct_upload) before executing */
+int fhestr_graph_input_chars(fhestr_graph* g, uint32_t count, uint32_t* ids, uint32_t* slots);
+/* FheAsciiChar::encrypt_trivial (fheasciichar.rs:17-25) */
+int fhestr_graph_trivial_chars(fhestr_graph* g, const uint8_t* values, uint32_t count, uint32_t* ids);
+int fhestr_graph_char_op(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t* out);
+/* fast != 0: depth-minimised recording (same plaintext for every input); 0: the reference's op order.
+ * Results: a string (out_chars/out_len, capacity out_cap) and/or a single char (*out_char), by method.
+ * The reference's panics ("Maximum supported size for find reached") come back as FHESTR_E_INVALID. */
+int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+                           uint64_t clear_n, uint32_t* out_chars, uint32_t out_cap, uint32_t* out_len,
+                           uint32_t* out_char);
+int fhestr_graph_mark_output(fhestr_graph* g, const uint32_t* ids, uint32_t count);
+/* levelise everything the marked outputs need; slot_align = number of ranks the levels will be sharded over */
+int fhestr_graph_compile(fhestr_graph* g, uint32_t slot_align, fhestr_graph_info* info);
+/* the compiled job list (for inspection, tests, or a caller that drives fhestr_program_* itself) */
+int fhestr_graph_get_program(const fhestr_graph* g, fhestr_job* jobs, uint32_t* level_offsets /* n_levels+1 */,
+                             uint32_t* level_pbs, uint32_t* level_first_dst);
+int fhestr_graph_get_luts(const fhestr_graph* g, uint8_t* tables /* [n_luts][16], graph-local ids */);
+int fhestr_graph_get_trivials(const fhestr_graph* g, uint32_t* slots, uint8_t* values);
+int fhestr_graph_char_slots(const fhestr_graph* g, const uint32_t* ids, uint32_t count, uint32_t* slots /* [count][4] */);
+/* run the compiled levels on the engine (registers LUTs, writes trivial outputs, shards each level over
+ * `world` ranks and, when the engine has a communicator, all-gathers each level's results), then commit:
+ * computed chars become inputs of whatever is recorded next */
+int fhestr_graph_execute(fhestr_graph* g, fhestr_engine* e, uint32_t rank, uint32_t world);
+/* the same split in two, for callers that time or interleave the run themselves */
+int fhestr_graph_bind(fhestr_graph* g, fhestr_engine* e, fhestr_program** out);
+int fhestr_graph_commit(fhestr_graph* g);
+
+/* ---- multi-GPU: one process per GPU, keys replicated, one in-place NCCL all-gather per level ----------- */
+/* unique_id: 128 bytes from fhestr_comm_unique_id on rank 0, handed to the other ranks by the host */
+int fhestr_comm_unique_id(void* unique_id_128);
+int fhestr_comm_init(fhestr_engine* e, uint32_t rank, uint32_t world, const void* unique_id_128);
+int fhestr_comm_destroy(fhestr_engine* e);
+/* the slice of a level's n_jobs PBS jobs that `rank` of `world` computes: [lo, hi), per = ceil(n_jobs/world)
+ * (the all-gather moves `per` blocks per rank, so a level's result slots are padded to per*world) */
+void fhestr_shard_range(uint32_t n_jobs, uint32_t rank, uint32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per);
 
 /* ---- test / measurement hooks ------------------------------------------------------------------ */
 /* keyswitch only: small-key LWEs [n_jobs][n+1] to host (bit-exact check against the oracle) */
