@@ -32,6 +32,7 @@ struct fhestr_engine {
     bool keys_loaded = false;
     u64* luts = nullptr;
     int n_luts = 0, cap_luts = 256;
+    std::vector<std::vector<uint8_t>> lut_tables;   // host copy: identical tables share one id
     // per-batch scratch (grown on demand)
     fhestr_job* d_jobs = nullptr;
     size_t jobs_cap = 0;
@@ -254,14 +255,26 @@ static int stage_bytes(fhestr_engine* e, const uint8_t* host, size_t n) {
 
 int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id) {
     if (!e || !table || !lut_id) return FHESTR_E_INVALID;
-    if (e->n_luts >= e->cap_luts) return fail(e, FHESTR_E_STATE, "LUT registry full");
     CK(cudaSetDevice(e->device));
     const int entries = 1 << (63 - e->prm.delta_log);
+    const std::vector<uint8_t> key(table, table + entries);
+    for (int i = 0; i < e->n_luts; i++)
+        if (e->lut_tables[i] == key) { *lut_id = i; return FHESTR_OK; }
+    if (e->n_luts >= e->cap_luts) {  // grow the registry (ids stay valid)
+        u64* bigger = nullptr;
+        CK(cudaMalloc(&bigger, (size_t)e->cap_luts * 2 * kN * sizeof(u64)));
+        CK(cudaMemcpyAsync(bigger, e->luts, (size_t)e->n_luts * kN * sizeof(u64), cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaFree(e->luts));
+        e->luts = bigger;
+        e->cap_luts *= 2;
+    }
     int rc = stage_bytes(e, table, entries);
     if (rc) return rc;
     e->launches += launch_lut_poly(e->d_bytes, entries, e->prm.delta_log, e->luts + (size_t)e->n_luts * kN, e->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));  // d_bytes is reused by the next call
+    e->lut_tables.push_back(key);
     *lut_id = e->n_luts++;
     return FHESTR_OK;
 }
@@ -352,8 +365,9 @@ int fhestr_pbs_batch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_jobs) 
 
 int fhestr_program_create(fhestr_engine* e, const fhestr_job* jobs, const uint32_t* level_offsets,
                           uint32_t n_levels, fhestr_program** out) {
-    if (!e || !jobs || !level_offsets || !out) return FHESTR_E_INVALID;
+    if (!e || !level_offsets || !out) return FHESTR_E_INVALID;
     const uint32_t total = level_offsets[n_levels];
+    if (!jobs && total) return fail(e, FHESTR_E_INVALID, "null job list");
     int rc = validate_jobs(e, jobs, total);
     if (rc) return rc;
     CK(cudaSetDevice(e->device));

@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's public interface, over the engine's C ABI.
+
+Same names, argument meaning and error behaviour as the reference so that parity tests read like its
+own tests (/root/reference/src/main.rs:127-157):
+
+    MyClientKey      /root/reference/src/client_key.rs:9-106
+    MyServerKey      /root/reference/src/server_key/mod.rs:13-1876, trim.rs
+    FheAsciiChar     /root/reference/src/ciphertext/fheasciichar.rs:7-168
+    FheString        /root/reference/src/ciphertext/fhestring.rs:5-90
+    FheStrip         /root/reference/src/ciphertext/fhestrip.rs:4-24
+
+What differs is WHEN work happens: every FheAsciiChar method and every MyServerKey method RECORDS into the
+op graph (fhestr_graph_*); decrypting (or MyServerKey.flush) compiles everything recorded so far into
+dependency levels of independent PBS jobs and runs them on the GPU.  Nothing here computes on ciphertexts
+in Python and there is no CPU path: without libfhestr_engine.so and a B200 the server key cannot be built.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .client import ClientKey
+from .engine import Engine, PARAM_MESSAGE_2_CARRY_2_KS_PBS
+from .graph import Graph
+
+MAX_BLOCKS = 4          # /root/reference/src/main.rs:23
+STRING_PADDING = 1      # /root/reference/src/main.rs:12
+MAX_REPETITIONS = 16    # /root/reference/src/main.rs:17
+MAX_FIND_LENGTH = 255   # /root/reference/src/main.rs:20
+
+
+class PublicParameters:
+    """public_parameters.rs:4-17 -- carried everywhere by the reference and never used (fheasciichar.rs:22)"""
+
+    def __init__(self, num_blocks: int = MAX_BLOCKS):
+        self.num_blocks = num_blocks
+
+
+class FheAsciiChar:
+    """One encrypted u8 = 4 radix blocks.  Either a fresh host ciphertext (`ct`, from the client) or a value
+    of a server key's graph (`sk`, `id`), or both once a fresh ciphertext has been handed to a server key."""
+
+    __slots__ = ("ct", "sk", "id")
+
+    def __init__(self, ct=None, sk=None, id=None):
+        self.ct, self.sk, self.id = ct, sk, id
+
+    @staticmethod
+    def encrypt_trivial(value: int, public_parameters, server_key: "MyServerKey") -> "FheAsciiChar":  # :17-25
+        return server_key._trivial(value)
+
+    def _bin(self, op, server_key, other):
+        return server_key._char_op(op, self, other)
+
+    def eq(self, server_key, other): return self._bin("eq", server_key, other)          # :35
+    def ne(self, server_key, other): return self._bin("ne", server_key, other)          # :40
+    def le(self, server_key, other): return self._bin("le", server_key, other)          # :45
+    def lt(self, server_key, other): return self._bin("lt", server_key, other)          # :50
+    def ge(self, server_key, other): return self._bin("ge", server_key, other)          # :55
+    def gt(self, server_key, other): return self._bin("gt", server_key, other)          # :60
+    def bitand(self, server_key, other): return self._bin("bitand", server_key, other)  # :65
+    def bitor(self, server_key, other): return self._bin("bitor", server_key, other)    # :74
+    def sub(self, server_key, other): return self._bin("sub", server_key, other)        # :83
+    def add(self, server_key, other): return self._bin("add", server_key, other)        # :87
+
+    def if_then_else(self, server_key, true_value, false_value):                        # :93
+        return server_key._char_op("if_then_else", self, true_value, false_value)
+
+    def is_whitespace(self, server_key, public_parameters=None): return server_key._char_op("is_whitespace", self)  # :106
+    def is_uppercase(self, server_key, public_parameters=None): return server_key._char_op("is_uppercase", self)    # :132
+    def is_lowercase(self, server_key, public_parameters=None): return server_key._char_op("is_lowercase", self)    # :146
+    def flip(self, server_key, public_parameters=None): return server_key._char_op("flip", self)                    # :161
+
+
+class FheString:
+    """fhestring.rs:5-9: Vec<FheAsciiChar> (+ the trivial constant 32 the reference keeps as `cst`)"""
+
+    def __init__(self, chars):
+        self.bytes = list(chars)
+
+    @staticmethod
+    def from_vec(chars, public_parameters=None, server_key=None):
+        return FheString(chars)
+
+    def __len__(self): return len(self.bytes)
+    def __getitem__(self, i): return self.bytes[i]
+    def __iter__(self): return iter(self.bytes)
+    def push(self, c): self.bytes.append(c)
+
+
+class FheStrip:
+    """fhestrip.rs:4-7"""
+
+    def __init__(self, string: FheString, pattern_found: FheAsciiChar):
+        self.string, self.pattern_found = string, pattern_found
+
+    @staticmethod
+    def decrypt(strip: "FheStrip", client_key: "MyClientKey"):  # fhestrip.rs:15-23
+        return client_key.decrypt(strip.string), client_key.decrypt_char(strip.pattern_found)
+
+
+class MyClientKey:
+    """client_key.rs:9-106.  Host-side keygen / encrypt / decrypt through fhestr_client_* (seeded)."""
+
+    def __init__(self, client: ClientKey, num_blocks: int = MAX_BLOCKS):
+        assert num_blocks == MAX_BLOCKS
+        self.client = client
+        self.public_parameters = PublicParameters(num_blocks)
+        self._server_keys = None
+
+    @staticmethod
+    def from_params(params: dict | None = None, num_blocks: int = MAX_BLOCKS, seed: int = 1) -> "MyClientKey":  # :30-35
+        prm = dict(PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+        prm.update(params or {})
+        return MyClientKey(ClientKey(seed=seed, **prm), num_blocks)
+
+    def get_server_key(self, **kw) -> "MyServerKey":  # :37-39
+        if self._server_keys is None:
+            self._server_keys = self.client.server_keys()
+        p = self.client.params
+        kw.setdefault("params", {f: getattr(p, f) for f, _ in p._fields_})
+        return MyServerKey(self._server_keys[0], self._server_keys[1], **kw)
+
+    def get_public_parameters(self) -> PublicParameters:  # :41-43
+        return self.public_parameters
+
+    @staticmethod
+    def _check(string: str):
+        assert all(ord(ch) < 128 and ch != "\0" for ch in string), \
+            "The input string must only contain ascii letters and not include null characters"  # :52-55
+
+    def encrypt(self, string: str, padding: int, public_parameters=None, server_key=None) -> FheString:  # :45-65
+        self._check(string)
+        cts = self.client.encrypt_u8((string + "\0" * padding).encode("ascii"))
+        return FheString([FheAsciiChar(ct=cts[i]) for i in range(cts.shape[0])])
+
+    def encrypt_no_padding(self, string: str):  # :67-79
+        self._check(string)
+        cts = self.client.encrypt_u8(string.encode("ascii"))
+        return [FheAsciiChar(ct=cts[i]) for i in range(cts.shape[0])]
+
+    def encrypt_char(self, plain_char: int) -> FheAsciiChar:  # :85-87
+        return FheAsciiChar(ct=self.client.encrypt_u8(bytes([plain_char]))[0])
+
+    def _host_cts(self, chars) -> np.ndarray:
+        chars = list(chars)
+        out = np.zeros((len(chars), 4, self.client.big), np.uint64)
+        need = [i for i, c in enumerate(chars) if c.ct is None]
+        for i, c in enumerate(chars):
+            if c.ct is not None:
+                out[i] = c.ct
+        if need:
+            sk = chars[need[0]].sk
+            got = sk._download([chars[i] for i in need])
+            for k, i in enumerate(need):
+                out[i] = got[k]
+        return out
+
+    def decrypt_char(self, cipher_char: FheAsciiChar) -> int:  # :81-83
+        return int(self.client.decrypt_u8(self._host_cts([cipher_char]))[0])
+
+    def decrypt(self, cipher_string) -> str:  # :96-106 (truncates at the first NUL)
+        b = bytes(self.client.decrypt_u8(self._host_cts(cipher_string)))
+        cut = b.find(b"\0")
+        return (b if cut < 0 else b[:cut]).decode("utf-8")
+
+    def decrypt_padded(self, cipher_string) -> list[int]:
+        """all chars, NULs included (what the plaintext oracle returns)"""
+        return [int(v) for v in self.client.decrypt_u8(self._host_cts(cipher_string))]
+
+
+class MyServerKey:
+    """server_key/mod.rs:13-16 -- instead of holding a tfhe::integer::ServerKey it owns the engine (device
+    key store + ciphertext arena) and the op graph.  `fast` selects the depth-minimised recording of the
+    string methods (same plaintext for every input); fast=False issues the reference's own op order."""
+
+    def __init__(self, bsk_std, ksk, params=None, device: int = 0, arena_blocks: int = 1 << 16, fast: bool = True,
+                 rank: int = 0, world: int = 1, engine: Engine | None = None):
+        self.engine = engine or Engine(arena_blocks=arena_blocks, device=device, **(params or {}))
+        if engine is None:
+            self.engine.load_keys(bsk_std, ksk)
+        self.fast, self.rank, self.world = fast, rank, world
+        self.key = self  # the reference passes `&my_server_key.key` around (main.rs:146)
+        self.graph = Graph()
+        self.last_info = None
+
+    def reset(self):
+        """drop everything recorded and reuse the arena from slot 0 (one query = one graph)"""
+        self.graph.close()
+        self.graph = Graph()
+
+    # ---- plumbing between host ciphertexts, graph ids and the arena
+    def _adopt(self, c: FheAsciiChar) -> int:
+        if c.id is not None and c.sk is self:
+            return c.id
+        assert c.ct is not None, "char belongs to another server key"
+        ids, slots = self.graph.input_chars(1)
+        for b in range(4):
+            self.engine.upload(int(slots[0, b]), c.ct[b])
+        c.sk, c.id = self, int(ids[0])
+        return c.id
+
+    def _adopt_all(self, chars):
+        chars = list(chars)
+        fresh = [c for c in chars if not (c.id is not None and c.sk is self)]
+        if fresh:
+            ids, slots = self.graph.input_chars(len(fresh))
+            cts = np.stack([c.ct for c in fresh]).reshape(-1, self.engine.big)
+            flat = slots.reshape(-1)
+            # input slots are handed out consecutively: one upload
+            assert (np.diff(flat.astype(np.int64)) == 1).all()
+            self.engine.upload(int(flat[0]), cts)
+            for c, i in zip(fresh, ids):
+                c.sk, c.id = self, int(i)
+        return np.array([c.id for c in chars], np.uint32)
+
+    def _wrap(self, cid: int) -> FheAsciiChar:
+        return FheAsciiChar(sk=self, id=int(cid))
+
+    def _trivial(self, value: int) -> FheAsciiChar:
+        return self._wrap(self.graph.trivial_chars([value & 255])[0])
+
+    def _char_op(self, op, a, b=None, c=None) -> FheAsciiChar:
+        ids = [int(self._adopt(x)) for x in (a, b, c) if x is not None]
+        return self._wrap(self.graph.char_op(op, *ids))
+
+    def flush(self, outputs):
+        """compile and run everything `outputs` depend on"""
+        ids = np.array([c.id for c in outputs], np.uint32)
+        self.graph.mark_output(ids)
+        self.last_info = self.graph.compile(self.world)
+        if self.last_info.slots_used > self.engine.arena_blocks:
+            raise MemoryError(f"graph needs {self.last_info.slots_used} arena blocks, engine has {self.engine.arena_blocks}")
+        self.graph.execute(self.engine, self.rank, self.world)
+
+    def _download(self, chars) -> np.ndarray:
+        self.flush(chars)
+        slots = self.graph.char_slots(np.array([c.id for c in chars], np.uint32))
+        out = np.zeros((len(chars), 4, self.engine.big), np.uint64)
+        flat = slots.reshape(-1).astype(np.int64)
+        if len(flat) and (np.diff(flat) == 1).all():
+            out[:] = self.engine.download(int(flat[0]), len(flat)).reshape(out.shape)
+        else:
+            for i, s in enumerate(flat):
+                out.reshape(-1, self.engine.big)[i] = self.engine.download(int(s), 1)[0]
+        return out
+
+    def _str(self, method, *args, clear_n=0):
+        ids = [self._adopt_all(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a))
+               for a in args]
+        rs, rc = self.graph.string_op(method, ids, fast=self.fast, clear_n=clear_n)
+        s = None if rs is None else FheString([self._wrap(i) for i in rs])
+        c = None if rc is None else self._wrap(rc)
+        return s, c
+
+    def _clear(self, pattern: str):
+        return [self._trivial(ord(ch)) for ch in pattern]
+
+    # ---- the string methods (public_parameters is accepted and ignored, as in the reference)
+    def to_upper(self, string, public_parameters=None): return self._str("to_upper", string)[0]            # mod.rs:65
+    def to_lower(self, string, public_parameters=None): return self._str("to_lower", string)[0]            # mod.rs:110
+    def contains(self, string, needle, public_parameters=None): return self._str("contains", string, needle)[1]        # :151
+    def contains_clear(self, string, clear_needle, public_parameters=None): return self.contains(string, self._clear(clear_needle))  # :198
+    def ends_with(self, string, needle, public_parameters=None): return self._str("ends_with", string, needle)[1]      # :241
+    def ends_with_clear(self, string, clear_needle, public_parameters=None): return self.ends_with(string, self._clear(clear_needle))  # :303
+    def starts_with(self, string, pattern, public_parameters=None): return self._str("starts_with", string, pattern)[1]  # :344
+    def starts_with_clear(self, string, clear_pattern, public_parameters=None): return self.starts_with(string, self._clear(clear_pattern))  # :392
+    def is_empty(self, string, public_parameters=None): return self._str("is_empty", string)[1]            # :431
+    def len(self, string, public_parameters=None): return self._str("len", string)[1]                      # :478
+    def repeat_clear(self, string, repetitions: int, public_parameters=None): return self._str("repeat_clear", string, clear_n=repetitions)[0]  # :517
+    def repeat(self, string, repetitions, public_parameters=None): return self._str("repeat", string, repetitions)[0]  # :567
+    def replace(self, string, from_, to, public_parameters=None): return self._str("replace", string, from_, to)[0]     # :624
+    def replace_clear(self, string, clear_from, clear_to, public_parameters=None):                                      # :679
+        return self.replace(string, self._clear(clear_from), self._clear(clear_to))
+    def rfind(self, string, pattern, public_parameters=None): return self._find("rfind", string, pattern)  # :727
+    def rfind_clear(self, string, clear_pattern, public_parameters=None): return self.rfind(string, self._clear(clear_pattern))  # :813
+    def find(self, string, pattern, public_parameters=None): return self._find("find", string, pattern)    # :1010
+    def find_clear(self, string, clear_pattern, public_parameters=None): return self.find(string, self._clear(clear_pattern))  # :1075
+    def eq(self, string, other, public_parameters=None): return self._str("eq", string, other)[1]          # :1122
+    def ne(self, string, other, public_parameters=None): return self._str("ne", string, other)[1]          # :1178
+    def eq_ignore_case(self, string, other, public_parameters=None): return self._str("eq_ignore_case", string, other)[1]  # :1221
+    def strip_prefix(self, string, pattern, public_parameters=None): return FheStrip(*self._str("strip_prefix", string, pattern))  # :1261
+    def strip_suffix(self, string, pattern, public_parameters=None): return FheStrip(*self._str("strip_suffix", string, pattern))  # :1335
+    def strip_prefix_clear(self, string, clear_pattern, public_parameters=None): return self.strip_prefix(string, self._clear(clear_pattern))  # :1421
+    def strip_suffix_clear(self, string, clear_pattern, public_parameters=None): return self.strip_suffix(string, self._clear(clear_pattern))  # :1457
+    def lt(self, string, other, public_parameters=None): return self._str("lt", string, other)[1]          # :1577
+    def le(self, string, other, public_parameters=None): return self._str("le", string, other)[1]          # :1613
+    def gt(self, string, other, public_parameters=None): return self._str("gt", string, other)[1]          # :1649
+    def ge(self, string, other, public_parameters=None): return self._str("ge", string, other)[1]          # :1685
+    def replacen(self, string, from_, to, n, public_parameters=None): return self._str("replacen", string, from_, to, n)[0]  # :1729
+    def replacen_clear(self, string, clear_from, clear_to, clear_n: int, public_parameters=None):          # :1789
+        return self.replacen(string, self._clear(clear_from), self._clear(clear_to), self._trivial(clear_n))
+    def concatenate(self, string, other, public_parameters=None): return self._str("concatenate", string, other)[0]  # :1864
+    def trim_end(self, string, public_parameters=None): return self._str("trim_end", string)[0]            # trim.rs:36
+    def trim_start(self, string, public_parameters=None): return self._str("trim_start", string)[0]        # trim.rs:86
+    def trim(self, string, public_parameters=None): return self._str("trim", string)[0]                    # trim.rs:146
+
+    def _find(self, method, string, pattern):
+        from .engine import EngineError
+        try:
+            return self._str(method, string, pattern)[1]
+        except EngineError as ex:
+            if "Maximum supported size for find reached" in str(ex):
+                raise RuntimeError("Maximum supported size for find reached") from None  # the reference panics (mod.rs:743,1026)
+            raise
+
+
+def bubble_zeroes_right(server_key: MyServerKey, string: FheString) -> FheString:
+    """utils.rs:28-46"""
+    return server_key._str("bubble_zeroes_right", string)[0]

@@ -38,7 +38,8 @@ def run_program(graph, input_slots, input_blocks, values=None):
     jobs, off, npbs, first = graph.program()
     luts = graph.luts()
     if values is None:
-        values = np.zeros(info.slots_used, np.int64)
+        # unwritten arena slots hold garbage (whatever an earlier query left there), never a convenient 0
+        values = np.random.default_rng(info.slots_used).integers(0, 32, info.slots_used).astype(np.int64)
     elif len(values) < info.slots_used:
         values = np.concatenate([values, np.zeros(info.slots_used - len(values), np.int64)])
     values[np.asarray(input_slots, np.int64)] = np.asarray(input_blocks, np.int64)

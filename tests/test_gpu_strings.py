@@ -1,0 +1,176 @@
+"""End-to-end parity on the GPU through the reference-style API (fhestring_b200/fhestring.py over the C ABI):
+encrypt with the real PARAM_MESSAGE_2_CARRY_2_KS_PBS parameters, run the string method as batched PBS levels
+on the B200, decrypt, and compare with (i) the plaintext oracle of the REFERENCE algorithm and (ii) what Rust
+`std` returns (the reference's own unit-test expectation, tests/golden/reference_tests.json).  Integer
+results: bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import fhestring_plain as P
+from strcases import SIGNATURES, decode_result, encode_args, reference_cases
+
+pytestmark = pytest.mark.gpu
+
+ORACLE_FN = {m: getattr(P, "length" if m == "len" else m) for m in SIGNATURES}
+
+
+@pytest.fixture(scope="module")
+def keys(build_lib):
+    from fhestring_b200.fhestring import MyClientKey
+    ck = MyClientKey.from_params(seed=20)
+    sk = ck.get_server_key(arena_blocks=1 << 19)
+    pp = ck.get_public_parameters()
+    yield ck, sk, pp
+    sk.engine.close()
+
+
+def call_method(ck, sk, pp, method, args, padding):
+    """the reference test body: encrypt the arguments, call the server-key method, decrypt"""
+    kinds, rkind = SIGNATURES[method]
+    enc = []
+    for kind, a in zip(kinds, args):
+        if kind == "s":
+            enc.append(ck.encrypt(a, padding, pp, sk.key))
+        elif kind == "p":
+            enc.append(ck.encrypt_no_padding(a))
+        elif kind == "n":
+            enc.append(ck.encrypt_char(int(a)))
+        else:
+            enc.append(int(a))
+    res = getattr(sk, method)(*enc, pp)
+    if rkind == "u8":
+        return ck.decrypt_char(res)
+    if rkind == "str":
+        return ck.decrypt_padded(res)
+    return ck.decrypt_padded(res.string), ck.decrypt_char(res.pattern_found)
+
+
+@pytest.mark.parametrize("case", reference_cases(), ids=lambda c: c["name"])
+def test_reference_unit_tests_fast(keys, case):
+    ck, sk, pp = keys
+    sk.reset()
+    sk.fast = True
+    m = case["method"]
+    if isinstance(case["expect"], str) and case["expect"].startswith("panic"):
+        with pytest.raises(RuntimeError, match="Maximum supported size for find reached"):
+            call_method(ck, sk, pp, m, case["args"], case["padding"])
+        return
+    got = call_method(ck, sk, pp, m, case["args"], case["padding"])
+    assert decode_result(m, got) == case["expect"]                      # Rust std
+    ref = ORACLE_FN[m](*encode_args(m, case["args"], case["padding"]))  # the reference's algorithm
+    if SIGNATURES[m][1] == "str":
+        assert list(got) == list(ref)
+    elif SIGNATURES[m][1] == "u8":
+        assert int(got) == int(ref)
+
+
+FAITHFUL = ["valid_contains", "valid_ends_with", "valid_starts_with", "lowercase", "len", "find", "eq", "less_than",
+            "greater_equal", "cli_Replace", "cli_StripSuffix", "cli_TrimStart", "cli_Concatenate", "cli_Rfind"]
+
+
+@pytest.mark.parametrize("case", [c for c in reference_cases() if c["name"] in FAITHFUL], ids=lambda c: c["name"])
+def test_reference_unit_tests_faithful(keys, case):
+    """the reference's own op order (hundreds of tiny levels): same decrypted result"""
+    ck, sk, pp = keys
+    sk.reset()
+    sk.fast = False
+    try:
+        got = call_method(ck, sk, pp, case["method"], case["args"], case["padding"])
+    finally:
+        sk.fast = True
+    assert decode_result(case["method"], got) == case["expect"]
+
+
+def test_char_primitives_eager(keys):
+    """FheAsciiChar methods called one at a time, as the reference's sequential callers do (fheasciichar.rs:35-104)"""
+    from fhestring_b200.fhestring import FheAsciiChar
+    ck, sk, pp = keys
+    sk.reset()
+    a, b = ck.encrypt_char(0x61), ck.encrypt_char(0x7A)
+    one = FheAsciiChar.encrypt_trivial(1, pp, sk)
+    assert ck.decrypt_char(a.eq(sk, b)) == 0
+    assert ck.decrypt_char(a.ne(sk, b)) == 1
+    assert ck.decrypt_char(a.lt(sk, b)) == 1
+    assert ck.decrypt_char(a.ge(sk, b)) == 0
+    s = a.add(sk, b)
+    assert ck.decrypt_char(s) == (0x61 + 0x7A) & 255
+    d = a.sub(sk, b)
+    assert ck.decrypt_char(d) == (0x61 - 0x7A) & 255
+    # results of earlier executions feed later ones (commit keeps them in the arena)
+    assert ck.decrypt_char(s.sub(sk, d)) == ((0x61 + 0x7A) - (0x61 - 0x7A)) & 255
+    assert ck.decrypt_char(a.lt(sk, b).if_then_else(sk, a, b)) == 0x61
+    assert ck.decrypt_char(a.eq(sk, b).bitor(sk, one)) == 1
+    assert ck.decrypt_char(a.is_lowercase(sk)) == 1 and ck.decrypt_char(a.is_uppercase(sk)) == 0
+    assert ck.decrypt_char(ck.encrypt_char(0x0A).is_whitespace(sk)) == 1
+    assert ck.decrypt_char(a.eq(sk, a).flip(sk)) == 0
+
+
+def test_config3_eq_ge_le_64_chars(keys):
+    """BASELINE config 3: == / >= / <= on two 64-char strings (padding 1)"""
+    ck, sk, pp = keys
+    rng = random.Random(3)
+    a = "".join(chr(rng.randrange(0x20, 0x7F)) for _ in range(64))
+    variants = {
+        "equal": a,
+        "differ_at_0": chr(0x20 + (ord(a[0]) - 0x1F) % 0x5F) + a[1:],
+        "differ_at_63": a[:63] + chr(0x20 + (ord(a[63]) - 0x1F) % 0x5F),
+        "prefix_48": a[:48],
+    }
+    for name, b in variants.items():
+        for m in ("eq", "ge", "le"):
+            sk.reset()
+            got = call_method(ck, sk, pp, m, [a, b], 1)
+            std = {"eq": a == b, "ge": a >= b, "le": a <= b}[m]
+            ref = ORACLE_FN[m](*encode_args(m, [a, b], 1))
+            assert got == int(std) == ref, (name, m)
+
+
+def test_config4_contains_find_256_chars(keys):
+    """BASELINE config 4: encrypted 8-char pattern over a 256-char encrypted string (L = 257 < 255 + 8)"""
+    ck, sk, pp = keys
+    rng = random.Random(4)
+    pat = "qzjxkvwq"
+    for where in (0, 124, 248, None):
+        body = [rng.choice("abcdefghilmnoprstu") for _ in range(256)]
+        if where is not None:
+            body[where:where + 8] = pat
+        s = "".join(body)
+        assert (s.find(pat) if where is not None else -1) == (where if where is not None else -1)
+        sk.reset()
+        es, ep = ck.encrypt(s, 1, pp, sk.key), ck.encrypt_no_padding(pat)
+        c, f = sk.contains(es, ep, pp), sk.find(es, ep, pp)
+        assert ck.decrypt_char(c) == int(where is not None)
+        assert ck.decrypt_char(f) == (where if where is not None else 255)
+        assert sk.last_info.n_levels <= 10
+
+
+def test_config5_replace_1024_chars(keys):
+    """BASELINE config 5: replace with encrypted from/to (4 chars each) over a 1024-char padded string"""
+    ck, sk, pp = keys
+    rng = random.Random(5)
+    body = [rng.choice("abcdfghijkmnpqrstuvwxyz ") for _ in range(1000)]
+    for pos in (0, 100, 333, 500, 640, 801, 900, 996):
+        body[pos:pos + 4] = "ello"
+    s = "".join(body)
+    sk.reset()
+    es = ck.encrypt(s, 24, pp, sk.key)
+    res = sk.replace(es, ck.encrypt_no_padding("ello"), ck.encrypt_no_padding("_llo"), pp)
+    got = ck.decrypt_padded(res)
+    assert len(got) == 1025
+    assert P.decrypt_str(got) == s.replace("ello", "_llo")
+    assert got == P.replace(encode_args("replace", [s, "ello", "_llo"], 24)[0], [ord(c) for c in "ello"], [ord(c) for c in "_llo"])
+
+
+def test_noise_of_deep_graph_outputs(keys):
+    """phase error of the result blocks of a long dependent chain stays inside the decoding margin (delta/2 = 2^58)
+    with room to spare: |err| < 2^55 (an 8-sigma bound for the parameter set's PBS output noise 2^-15.5 is 2^51.5)"""
+    ck, sk, pp = keys
+    sk.reset()
+    s = ck.encrypt("hello world", 1, pp, sk.key)
+    up = sk.to_upper(sk.to_lower(sk.to_upper(s, pp), pp), pp)
+    cts = ck._host_cts(up.bytes)
+    vals, err = ck.client.decrypt_blocks(cts.reshape(-1, ck.client.big), with_error=True)
+    assert ck.decrypt(up) == "HELLO WORLD"
+    assert np.abs(err).max() < (1 << 55)
