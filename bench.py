@@ -113,7 +113,77 @@ def cpu_port_rate(seconds_target: float = 12.0):
     return count / dt, th, f"{count} of the {BATCH} blocks, {dt:.1f} s, oracle f64-FFT PBS (OpenMP over ciphertexts)"
 
 
-def reference_arm(args):
+def contains_leg(eng, ck, stream, rank, world, steps, barrier):
+    """BASELINE metric, second half: contains() latency on a 256-char encrypted string with an encrypted 8-char
+    pattern (config 4; /root/reference/src/server_key/mod.rs:151-182), recorded depth-minimised, every level's
+    PBS jobs sharded over the ranks with one in-place NCCL all-gather per level (strong scaling)."""
+    import ctypes as C
+    import torch
+    from fhestring_b200.graph import Graph
+    rng = np.random.default_rng(4)
+    body = rng.choice(list(b"abcdefghilmnoprstu"), 256).astype(np.uint8)
+    pat = np.frombuffer(b"qzjxkvwq", np.uint8)
+    body[124:132] = pat
+    s = np.concatenate([body, np.zeros(1, np.uint8)])           # STRING_PADDING = 1 (main.rs:12)
+    out = {}
+    cts = torch.from_numpy(ck.encrypt_u8(np.concatenate([s, pat])).reshape(-1, eng.big)).pin_memory()
+    n_in = cts.shape[0]
+    in_ptr = C.cast(cts.data_ptr(), C.POINTER(C.c_uint64))
+    eng._ck(eng.lib.fhestr_ct_upload(eng.h, C.c_uint32(0), C.c_uint32(n_in), in_ptr))
+    eng.sync()
+    for name, want in (("contains", 1), ("find", 124)):
+        g = Graph()                                              # one query = one graph (slots restart at 0)
+        ids_s, slots_s = g.input_chars(len(s))
+        ids_p, slots_p = g.input_chars(len(pat))
+        assert int(slots_s[0, 0]) == 0 and int(slots_p[-1, -1]) == n_in - 1
+        _, cid = g.string_op(name, [ids_s, ids_p], fast=True)
+        g.mark_output([cid])
+        info = g.compile(world)
+        prog = g.bind(eng)
+        res_slots = [int(x) for x in g.char_slots([cid])[0]]
+        host_res = torch.zeros((4, eng.big), dtype=torch.int64).pin_memory()
+        res_ptrs = [C.cast(host_res[blk].data_ptr(), C.POINTER(C.c_uint64)) for blk in range(4)]
+        for _ in range(2):
+            prog.run(rank=rank, world=world)
+        barrier()
+        dev, e2e = [], []
+        for _ in range(max(3, steps)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record(stream)
+            prog.run(rank=rank, world=world)
+            b.record(stream)
+            barrier()
+            dev.append(a.elapsed_time(b))
+        for _ in range(max(3, steps)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record(stream)
+            eng._ck(eng.lib.fhestr_ct_upload(eng.h, C.c_uint32(0), C.c_uint32(n_in), in_ptr))
+            prog.run(rank=rank, world=world)
+            for blk in range(4):   # the result char: 4 radix blocks, each its own arena slot
+                eng._ck(eng.lib.fhestr_ct_download(eng.h, C.c_uint32(res_slots[blk]), C.c_uint32(1), res_ptrs[blk]))
+            b.record(stream)
+            barrier()
+            e2e.append(a.elapsed_time(b))
+        got = int(ck.decrypt_u8(host_res.numpy().view(np.uint64).reshape(1, 4, eng.big))[0])
+        t = torch.tensor([float(np.median(dev)), float(np.median(e2e))], device="cuda", dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        jobs, off, npbs, _ = g.program()
+        out[name] = {"latency_ms": float(t[0]), "e2e_latency_ms": float(t[1]), "levels": int(info.n_levels),
+                     "pbs": int(info.n_pbs), "level_pbs": [int(x) for x in npbs], "decrypted": got, "expected": want,
+                     "verified": bool(got == want), "h2d_bytes": int(n_in * eng.big * 8), "d2h_bytes": int(4 * eng.big * 8)}
+        prog.close()
+        g.close()
+    out["workload"] = ("contains/find, encrypted 8-char pattern over a 256-char encrypted string (+1 NUL padding), "
+                       "depth-minimised graph, levels sharded over the ranks, NCCL all-gather per level")
+    out["reference_graph"] = {"contains_pbs_nominal": 19000, "contains_levels": 260, "source": "SURVEY.md 2.6"}
+    return out
+
+
+def reference_arm(args, out):
     """--impl reference: the reference's own CPU implementation is tfhe-rs (Rust, not buildable here: no
     cargo, crate not vendored), so this times the oracle port of the same f64-FFT algorithm."""
     rank = int(os.environ.get("RANK", "0"))
@@ -135,10 +205,20 @@ def reference_arm(args):
         "cpu_baseline": {"value": v, "unit": "PBS/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=out, flush=True)
+
+
+def _claim_stdout():
+    """the contract is ONE JSON line on stdout: keep a private handle to it and point fd 1 at stderr so that
+    library banners (NCCL prints its version on stdout) cannot pollute it"""
+    sys.stdout.flush()
+    keep = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return keep
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -146,9 +226,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-contains", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, out)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -169,7 +250,7 @@ def main():
     # ---- setup (untimed): keys, ciphertexts, engine
     ck = ClientKey(seed=1)
     bsk, ksk = ck.server_keys()
-    eng = Engine(arena_blocks=2 * B + 8, device=local)
+    eng = Engine(arena_blocks=max(2 * B + 8, 1 << 15), device=local)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -239,6 +320,13 @@ def main():
     e2e_verified = bool(np.array_equal(ck.decrypt_blocks(host_out.numpy()), want))
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- string leg: contains()/find() latency, levels sharded over the ranks
+    contains = None
+    if not args.no_contains:
+        if world > 1:
+            eng.comm_init(rank, world)
+        contains = contains_leg(eng, ck, stream, rank, world, args.steps, barrier)
+
     # ---- max over ranks
     t = torch.tensor([ms_total, e2e_ms, br_ms], device="cuda", dtype=torch.float64)
     ok = torch.tensor([int(verified and e2e_verified)], device="cuda")
@@ -279,10 +367,12 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
         }
+        if contains is not None:
+            line["contains_256"] = contains
         if not args.no_cpu_baseline:
             v, cores, sample = cpu_port_rate(12.0)
             line["cpu_baseline"] = {"value": v, "unit": "PBS/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -65,6 +65,7 @@ def load_library() -> C.CDLL:
     lib.fhestr_engine_destroy.argtypes = [C.c_void_p]
     lib.fhestr_program_destroy.restype = None
     lib.fhestr_program_destroy.argtypes = [C.c_void_p]
+    lib.fhestr_shard_range.restype = None
     return lib
 
 
@@ -157,6 +158,30 @@ class Engine:
         nl, npbs = C.c_uint64(), C.c_uint64()
         self._ck(self.lib.fhestr_get_timing(self.h, C.byref(ks), C.byref(br), C.byref(nl), C.byref(npbs)))
         return ks.value, br.value, int(nl.value), int(npbs.value)
+
+    # -- multi-GPU: one process per GPU, the engine's own NCCL communicator (fhestr_comm_*)
+    def comm_init(self, rank: int, world: int):
+        """rank 0 creates the NCCL unique id, torch.distributed (any backend) carries it to the other ranks"""
+        import torch
+        import torch.distributed as dist
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            self._ck(self.lib.fhestr_comm_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        t = torch.from_numpy(uid)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        uid = np.ascontiguousarray(t.cpu().numpy())
+        self._ck(self.lib.fhestr_comm_init(self.h, C.c_uint32(rank), C.c_uint32(world), uid.ctypes.data_as(C.c_void_p)))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self._ck(self.lib.fhestr_comm_destroy(self.h))
+
+    def shard_range(self, n_jobs: int, rank: int, world: int):
+        lo, hi, per = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.fhestr_shard_range(C.c_uint32(n_jobs), C.c_uint32(rank), C.c_uint32(world), C.byref(lo), C.byref(hi), C.byref(per))
+        return lo.value, hi.value, per.value
 
     # -- keys / LUTs
     def load_keys(self, bsk_std: np.ndarray, ksk: np.ndarray):
