@@ -1,10 +1,10 @@
 // blind_rotate.cu -- K2+K3+K4 for sm_100a: modulus switch, blind rotation (742 CMUX steps), sample
 // extract, one launch per dependency level.  The per-thread program is br_core.cuh.
 //
-// Mapping: one PBS = one pair of warps (mask polynomial, body polynomial); a CTA carries P pairs
-// (P = 4 fills the 64K-register file at 255 registers/thread: 8 warps, 2 per SM sub-partition).
-// Shared memory per pair: accumulator 2 x 2048 u64 (32 KiB) + two padded transpose buffers
-// (2 x 8448 B) + the mod-switched mask (2 KiB) = 51 712 B; 4 pairs = 202 KiB of the 227 KiB.
+// Mapping: one PBS = one pair of warps (mask polynomial, body polynomial), one PBS per 64-thread CTA, 4 CTAs
+// per SM (255 registers/thread fill the 64K-register file: 8 warps, 2 per SM sub-partition).
+// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + two padded transpose
+// buffers (2 x 8448 B) + the mod-switched mask (2 KiB) = 35 328 B.
 // The Fourier BSK (46 MiB for n = 742) stays resident in the 126 MB L2 and is read with 16-byte
 // read-only loads, one 64 KiB step tile per CMUX.
 #include "kernels.cuh"
@@ -12,17 +12,18 @@
 namespace fhestr {
 
 constexpr int kAtildeBytes = 2048;  // up to 1024 u16
-constexpr int kPairSmemBytes = 2 * kN * 8 + 2 * kXbufDoubles * 8 + kAtildeBytes;
+constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
+constexpr int kPairSmemBytes = kAccBytes + 2 * kXbufDoubles * 8 + kAtildeBytes;
 
 struct DevCtx {
     int lane_, poly_, slot_;
-    u64* acc_;
+    acc_t* acc_;
     double* xbuf_;
     double* xbuf_partner_;
     uint16_t* atilde_;
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ int poly() const { return poly_; }
-    __device__ __forceinline__ u64* acc() { return acc_; }
+    __device__ __forceinline__ acc_t* acc() { return acc_; }
     __device__ __forceinline__ double* xbuf() { return xbuf_; }
     __device__ __forceinline__ double* xbuf_partner() { return xbuf_partner_; }
     __device__ __forceinline__ uint16_t* atilde() { return atilde_; }
@@ -36,16 +37,17 @@ struct DevCtx {
     }
 };
 
-template <int P>
-__global__ void __launch_bounds__(64 * P, 1) blind_rotate_kernel(BrBatchArgs A) {
+// P = PBS per CTA, MB = CTAs per SM the register allocation is sized for (launch bound)
+template <int P, int MB>
+__global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     const int slot = warp >> 1;
     const int b = blockIdx.x * P + slot;
     if (b >= A.B) return;  // whole pair leaves together; pair barriers are per pair
     unsigned char* base = smem + (size_t)slot * kPairSmemBytes;
-    u64* acc = reinterpret_cast<u64*>(base);
-    double* xb = reinterpret_cast<double*>(base + 2 * kN * 8);
+    acc_t* acc = reinterpret_cast<acc_t*>(base);
+    double* xb = reinterpret_cast<double*>(base + kAccBytes);
     DevCtx c;
     c.lane_ = threadIdx.x & 31;
     c.poly_ = warp & 1;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(64 * P, 1) blind_rotate_kernel(BrBatchArgs A) 
     c.acc_ = acc + c.poly_ * kN;
     c.xbuf_ = xb + c.poly_ * kXbufDoubles;
     c.xbuf_partner_ = xb + (1 - c.poly_) * kXbufDoubles;
-    c.atilde_ = reinterpret_cast<uint16_t*>(base + 2 * kN * 8 + 2 * kXbufDoubles * 8);
+    c.atilde_ = reinterpret_cast<uint16_t*>(base + kAccBytes + 2 * kXbufDoubles * 8);
 
     BrJobView job;
     job.n = A.n;
@@ -66,25 +68,32 @@ __global__ void __launch_bounds__(64 * P, 1) blind_rotate_kernel(BrBatchArgs A) 
     br_thread_main(c, job, A.bsk, A.tf, A.ti);
 }
 
-cudaError_t blind_rotate_configure() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 * kPairSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPairSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPairSmemBytes);
-    return e;
+template <int P, int MB>
+static cudaError_t configure_one() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<P, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, P * kPairSmemBytes);
 }
 
+cudaError_t blind_rotate_configure() {
+    cudaError_t e;
+    if ((e = configure_one<1, 4>()) != cudaSuccess) return e;
+    if ((e = configure_one<2, 2>()) != cudaSuccess) return e;
+    return configure_one<4, 1>();
+}
+
+// pbs_per_cta: 0 = default (1).  Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255
+// registers is the fastest shape; independent CTAs drift out of phase and overlap their FP64 and shared-memory
+// phases, while 2 or 4 PBS per CTA run in lockstep (1.3-1.5x slower), and sizing the register allocation for
+// 5-6 CTAs per SM (168 registers) makes every warp ~1.6x slower for 1.5x the warps (net 0.8x).
 int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s) {
     if (a.B <= 0) return 0;
     int P = pbs_per_cta;
-    if (P != 1 && P != 2 && P != 4) P = 1;  // measured: independent 64-thread CTAs drift out of phase and overlap FP64 with shared-memory phases; P=4 runs in lockstep and is 1.47x slower
+    if (P != 1 && P != 2 && P != 4) P = 1;
     const int grid = (a.B + P - 1) / P;
+    const int smem = P * kPairSmemBytes;
     switch (P) {
-        case 1: blind_rotate_kernel<1><<<grid, 64, 1 * kPairSmemBytes, s>>>(a); break;
-        case 2: blind_rotate_kernel<2><<<grid, 128, 2 * kPairSmemBytes, s>>>(a); break;
-        default: blind_rotate_kernel<4><<<grid, 256, 4 * kPairSmemBytes, s>>>(a); break;
+        case 1: blind_rotate_kernel<1, 4><<<grid, 64, smem, s>>>(a); break;
+        case 2: blind_rotate_kernel<2, 2><<<grid, 128, smem, s>>>(a); break;
+        default: blind_rotate_kernel<4, 1><<<grid, 256, smem, s>>>(a); break;
     }
     return 1;
 }

@@ -57,30 +57,41 @@ FHE_HD uint32_t modswitch_2N(u64 x) {
     return (uint32_t)t & (2 * kN - 1);
 }
 
-// A.4 signed decomposition, one level of 23 bits: digit in (-2^22, 2^22]
-FHE_HD double digit23(u64 x) {
-    const uint32_t hi = (uint32_t)((x + (1ull << 40)) >> 32);
-    int32_t d = ((int32_t)hi) >> 9;
+// The accumulator lives on the 32-bit torus: acc_t = the top 32 bits of tfhe-rs' u64 torus words.  The
+// decomposition only ever looks at the top 23 bits (+ one rounding bit) of a difference, and what each CMUX
+// adds is known to about 2^-25 of the torus (f64 FFT round-off), so the 2^-33 rounding of a 32-bit word is
+// two orders of magnitude below the noise the step already has -- and it halves the accumulator's shared
+// memory (16 KiB per PBS instead of 32), its traffic and the integer work of every step.
+typedef uint32_t acc_t;
+
+FHE_HD acc_t acc_from_u64(u64 x) { return (acc_t)((x + (1ull << 31)) >> 32); }
+FHE_HD u64 acc_to_u64(acc_t a) { return (u64)a << 32; }
+
+// A.4 signed decomposition, one level of 23 bits, of a 32-bit torus difference: digit in (-2^22, 2^22]
+FHE_HD double digit23(acc_t x) {
+    int32_t d = ((int32_t)(x + (1u << 8))) >> 9;
     if (d == -(1 << 22)) d = (1 << 22);
     return (double)d;
 }
 
-// coefficient j of X^e * P (negacyclic), e in [0, 2N)
-FHE_HD u64 rot_coef(const u64* P, int j, int e) {
+// coefficient j of X^e * P (negacyclic), e in [0, 2N); generic word type
+template <class T>
+FHE_HD T rot_coef(const T* P, int j, int e) {
     const int q = (j - e) & (2 * kN - 1);
-    const u64 v = P[q & (kN - 1)];
-    return (q & kN) ? (u64)0 - v : v;
+    const T v = P[q & (kN - 1)];
+    return (q & kN) ? (T)0 - v : v;
 }
 
-// x in torus turns -> round(frac(x) * 2^64) as a wrapping u64
-FHE_HD u64 torus_from_double(double x) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: (x + magic) - magic == rint(x) for |x| < 2^51
+// x in units of 2^-32 turns -> round(x) mod 2^32 (the Fourier BSK carries the 2^-32 / M scale)
+FHE_HD acc_t torus32_from_double(double x) {
+    const double magic = 29014219670751100192948224.0;  // 1.5 * 2^84: (x + magic) - magic rounds x to a multiple of 2^32
     const double r = (x + magic) - magic;
-    const double f = (x - r) * 18446744073709551616.0;
+    const double f = x - r;                              // exact, |f| <= 2^31
 #ifdef __CUDA_ARCH__
-    return (u64)__double2ll_rn(f);
+    return (acc_t)__double2int_rn(f);                    // +2^31 saturates to 2^31 - 1: one ulp (2^-32), probability ~2^-20
 #else
-    return (u64)(i64)llrint(f);
+    const i64 v = (i64)llrint(f);
+    return (acc_t)(int32_t)(v > 2147483647LL ? 2147483647LL : v);
 #endif
 }
 
@@ -132,7 +143,7 @@ FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
 
 // Fourier BSK layout (engine-private, produced once by the key-conversion kernel):
 //   g[ ((((step*2 + row)*32 + k2)*2 + col)*32 + k1 ]   complex f64, k = k1 + 32 k2
-// scaled by 2^-64 / M so that the inverse transform directly yields torus turns.
+// scaled by 2^-32 / M so that the inverse transform directly yields units of 2^-32 turns (acc_t ulps).
 constexpr int kBskStepElems = 2 * 32 * 2 * 32;  // 4096 complex = 64 KiB per CMUX step
 FHE_HD int bsk_index(int row, int k2, int col, int k1) { return ((row * 32 + k2) * 2 + col) * 32 + k1; }
 
@@ -140,10 +151,10 @@ FHE_HD int bsk_index(int row, int k2, int col, int k1) { return ((row * 32 + k2)
 //   a[0..31]  = ACC[32 n1 + lane], a[32..63] = ACC[32 n1 + lane + M]  (registers, in/out)
 //   c.acc()   = this polynomial's accumulator in shared memory (same values), updated on exit
 template <class Ctx>
-FHE_HD void cmux_step(Ctx& c, u64 (&a)[64], int e, const cplx* g, const cplx* tf, const cplx* ti) {
+FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* tf, const cplx* ti) {
     const int t = c.lane();
     const int p = c.poly();
-    u64* acc = c.acc();
+    acc_t* acc = c.acc();
     double re[32], im[32];
     // rotate, subtract, decompose
 #pragma unroll
@@ -183,8 +194,8 @@ FHE_HD void cmux_step(Ctx& c, u64 (&a)[64], int e, const cplx* g, const cplx* tf
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
         const int j = 32 * n1 + t;
-        a[n1] = acc[j] + torus_from_double(re[n1]);
-        a[32 + n1] = acc[j + kM] + torus_from_double(im[n1]);
+        a[n1] = acc[j] + torus32_from_double(re[n1]);
+        a[32 + n1] = acc[j + kM] + torus32_from_double(im[n1]);
         acc[j] = a[n1];
         acc[j + kM] = a[32 + n1];
     }
@@ -195,7 +206,7 @@ FHE_HD void cmux_step(Ctx& c, u64 (&a)[64], int e, const cplx* g, const cplx* tf
 template <class Ctx>
 FHE_HD void bsk_poly_forward(Ctx& c, const u64* poly, cplx* out_step, int row, int col, const cplx* tf) {
     const int t = c.lane();
-    const double sc = 1.0 / (18446744073709551616.0 * (double)kM);
+    const double sc = 1.0 / (4294967296.0 * (double)kM);   // 2^-64 (u64 -> turns) * 2^32 (turns -> acc_t ulps) / M
     double re[32], im[32];
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
@@ -228,8 +239,8 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
     uint16_t* at = c.atilde();
     for (int idx = p * 32 + t; idx <= n; idx += 64) at[idx] = (uint16_t)modswitch_2N(job.ks[idx]);
     c.pair_sync();
-    u64* acc = c.acc();
-    u64 a[64];
+    acc_t* acc = c.acc();
+    acc_t a[64];
     {
         const int e0 = (2 * kN - (int)at[n]) & (2 * kN - 1);
 #pragma unroll
@@ -238,8 +249,8 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
             u64 v;
             if (job.init_acc) v = job.init_acc[p * kN + j];
             else v = (p == 1) ? rot_coef(job.lut, j, e0) : (u64)0;
-            a[m] = v;
-            acc[j] = v;
+            a[m] = acc_from_u64(v);   // LUT words are multiples of 2^59: exact
+            acc[j] = a[m];
         }
     }
     c.syncwarp();
@@ -250,17 +261,17 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
     }
     if (job.out_acc) {
 #pragma unroll
-        for (int m = 0; m < 64; m++) job.out_acc[p * kN + 32 * m + t] = a[m];
+        for (int m = 0; m < 64; m++) job.out_acc[p * kN + 32 * m + t] = acc_to_u64(a[m]);
     }
     if (job.out_lwe) {
         if (p == 0) {
 #pragma unroll
             for (int m = 0; m < 64; m++) {
                 const int j = 32 * m + t;
-                job.out_lwe[j] = (j == 0) ? acc[0] : (u64)0 - acc[kN - j];
+                job.out_lwe[j] = acc_to_u64((j == 0) ? acc[0] : (acc_t)0 - acc[kN - j]);
             }
         } else if (t == 0) {
-            job.out_lwe[kN] = acc[0];
+            job.out_lwe[kN] = acc_to_u64(acc[0]);
         }
     }
 }

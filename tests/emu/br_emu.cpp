@@ -13,7 +13,7 @@ using namespace fhestr;
 
 struct HostCtx {
     int lane_, poly_;
-    u64* acc_;
+    acc_t* acc_;
     double* xbuf_;
     double* xbuf_partner_;
     uint16_t* atilde_;
@@ -21,7 +21,7 @@ struct HostCtx {
     std::barrier<>* pair_bar;
     int lane() const { return lane_; }
     int poly() const { return poly_; }
-    u64* acc() { return acc_; }
+    acc_t* acc() { return acc_; }
     double* xbuf() { return xbuf_; }
     double* xbuf_partner() { return xbuf_partner_; }
     uint16_t* atilde() { return atilde_; }
@@ -57,7 +57,7 @@ void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc,
                       u64* out_lwe, u64* out_acc) {
     std::vector<cplx> tf(1024), ti(1024);
     make_twiddles(tf.data(), ti.data());
-    std::vector<u64> acc(2 * kN);
+    std::vector<acc_t> acc(2 * kN);
     std::vector<double> xbuf(2 * kXbufDoubles);
     std::vector<uint16_t> at(n + 64);
     std::barrier<> wb0(32), wb1(32), pb(64);

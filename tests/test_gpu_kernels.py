@@ -99,22 +99,28 @@ def test_single_external_product_tolerance(build_lib, small_oracle):
     eng.load_keys(keys.bsk[:1], np.ascontiguousarray(keys.ksk[:, :, [0, SMALL_N]]))
     rng = np.random.default_rng(3)
     es = [1, 777, 2048, 2048 + 5, 4095, 0]
-    glwe = rng.integers(0, 2**64, (len(es), 2, 2048), dtype=np.uint64)
-    glwe[1], glwe[3] = G["cmux_glwe"][0], G["cmux_glwe"][1]
+    # the oracle itself against the golden fixture (full 64-bit inputs)
+    with np.errstate(over="ignore"):
+        gd = monomial_mul(G["cmux_glwe"][0], 777) - G["cmux_glwe"][0]
+    assert np.array_equal(o.external_product_exact(keys.bsk[0], gd, G["cmux_glwe"][0]), G["cmux_exact"][0])
+    # the kernel keeps the accumulator on the 32-bit torus (br_core.cuh: acc_t): inputs are given at that
+    # resolution so that both sides decompose the same digits and the comparison isolates the FFT error
+    glwe = rng.integers(0, 2**64, (len(es), 2, 2048), dtype=np.uint64) & np.uint64(0xFFFFFFFF00000000)
+    glwe[1] = G["cmux_glwe"][0] & np.uint64(0xFFFFFFFF00000000)
     ks = np.zeros((len(es), 2), np.uint64)
     for b, e in enumerate(es):
         ks[b, 0] = np.uint64(e) << np.uint64(52)
     got = eng.debug_blind_rotate(ks, None, glwe)
+    assert not (got & np.uint64(0xFFFFFFFF)).any()
     for b, e in enumerate(es):
         with np.errstate(over="ignore"):
             diff = monomial_mul(glwe[b], e) - glwe[b]
         want = o.external_product_exact(keys.bsk[0], diff, glwe[b])
-        if e == 777:
-            assert np.array_equal(want, G["cmux_exact"][0])
         d = (got[b] - want).astype(np.int64).astype(float)
         if e == 0:
             assert not d.any()  # skipped step: exactly the input
             continue
+        # RMS <= 2^-24, max <= 2^-21 of the torus (f64 FFT round-off + the 2^-33 rounding to acc_t)
         assert np.sqrt(np.mean(d * d)) <= 2.0**40, (e, np.log2(np.sqrt(np.mean(d * d))))
         assert np.abs(d).max() <= 2.0**43, (e, np.log2(np.abs(d).max()))
     eng.close()
