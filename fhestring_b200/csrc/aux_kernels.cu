@@ -33,10 +33,10 @@ struct ConvCtx {
         return cplx{v.x, v.y};
     }
 };
-__global__ void __launch_bounds__(128) bsk_convert_kernel(const u64* bsk_std, int n_polys, const cplx* tf, cplx* out) {
-    __shared__ __align__(16) double xb[4][kXbufDoubles];
+__global__ void __launch_bounds__(64) bsk_convert_kernel(const u64* bsk_std, int n_polys, const cplx* tf, cplx* out) {
+    __shared__ __align__(16) double xb[2][kWarpXbufDoubles];
     const int warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * 4 + warp;  // polynomial index = (step*2 + row)*2 + col
+    const int q = blockIdx.x * 2 + warp;  // polynomial index = (step*2 + row)*2 + col
     if (q >= n_polys) return;
     ConvCtx c{(int)(threadIdx.x & 31), xb[warp]};
     const int step = q >> 2, row = (q >> 1) & 1, col = q & 1;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) bsk_convert_kernel(const u64* bsk_std, in
 }
 int launch_bsk_convert(const u64* bsk_std, int n, const cplx* tf, cplx* out, cudaStream_t s) {
     const int polys = n * 4;
-    bsk_convert_kernel<<<(polys + 3) / 4, 128, 0, s>>>(bsk_std, polys, tf, out);
+    bsk_convert_kernel<<<(polys + 1) / 2, 64, 0, s>>>(bsk_std, polys, tf, out);
     return 1;
 }
 

@@ -3,8 +3,8 @@
 //
 // Mapping: one PBS = one pair of warps (mask polynomial, body polynomial), one PBS per 64-thread CTA, 4 CTAs
 // per SM (255 registers/thread fill the 64K-register file: 8 warps, 2 per SM sub-partition).
-// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + two padded transpose
-// buffers (2 x 8448 B) + the mod-switched mask (2 KiB) = 35 328 B.
+// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + four padded transpose
+// matrices (re / im for each warp, 4 x 8448 B) + the mod-switched mask (2 KiB) = 52 224 B.
 // The Fourier BSK (46 MiB for n = 742) stays resident in the 126 MB L2 and is read with 16-byte
 // read-only loads, one 64 KiB step tile per CMUX.
 #include "kernels.cuh"
@@ -13,7 +13,7 @@ namespace fhestr {
 
 constexpr int kAtildeBytes = 2048;  // up to 1024 u16
 constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
-constexpr int kPairSmemBytes = kAccBytes + 2 * kXbufDoubles * 8 + kAtildeBytes;
+constexpr int kPairSmemBytes = kAccBytes + 2 * kWarpXbufDoubles * 8 + kAtildeBytes;  // 52 224 B: 4 PBS per SM
 
 struct DevCtx {
     int lane_, poly_, slot_;
@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     c.poly_ = warp & 1;
     c.slot_ = slot;
     c.acc_ = acc + c.poly_ * kN;
-    c.xbuf_ = xb + c.poly_ * kXbufDoubles;
-    c.xbuf_partner_ = xb + (1 - c.poly_) * kXbufDoubles;
-    c.atilde_ = reinterpret_cast<uint16_t*>(base + kAccBytes + 2 * kXbufDoubles * 8);
+    c.xbuf_ = xb + c.poly_ * kWarpXbufDoubles;
+    c.xbuf_partner_ = xb + (1 - c.poly_) * kWarpXbufDoubles;
+    c.atilde_ = reinterpret_cast<uint16_t*>(base + kAccBytes + 2 * kWarpXbufDoubles * 8);
 
     BrJobView job;
     job.n = A.n;

@@ -15,7 +15,7 @@
 //   twiddle Tf(k1,n2) = exp(i pi n2 (1-4 k1)/N), transpose through shared memory
 //   pass 2 (lane = k1, registers n2 -> k2): plain DFT-32 (fft32_fwd_p2)
 // ONE WARP owns one polynomial: 32 complex points per lane live in registers, the only exchange inside
-// a transform is one 32x32 transpose (done as two 8-byte halves through an 8.25 KB padded buffer), and
+// a transform is one 32x32 transpose (real and imaginary parts through two 8.25 KB padded buffers), and
 // only __syncwarp is needed.  The two warps of a PBS (mask polynomial, body polynomial) swap one
 // spectrum per step through the same buffers (pair barrier).  The inverse mirrors the forward and ends
 // in the layout the next step's forward starts from, so the new accumulator words stay in registers.
@@ -37,7 +37,8 @@ typedef long long i64;
 constexpr int kN = 2048;          // polynomial size
 constexpr int kM = 1024;          // complex points
 constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-free 64-bit column reads
-constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B per warp
+constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B: one padded 32 x 32 matrix
+constexpr int kWarpXbufDoubles = 2 * kXbufDoubles;  // per warp: one matrix for the real parts, one for the imaginary
 constexpr int kPbsBaseLog = 23;
 
 struct alignas(16) cplx { double x, y; };
@@ -95,16 +96,18 @@ FHE_HD acc_t torus32_from_double(double x) {
 #endif
 }
 
-// 32x32 transpose of one double per (lane, register) through the warp's padded buffer
+// 32x32 transpose of one complex point per (lane, register) through the warp's two padded buffers: all 64
+// stores, one __syncwarp, all 64 loads -- one exposed shared-memory round trip per transform
 template <class Ctx>
-FHE_HD void transpose32(Ctx& c, double (&v)[32]) {
+FHE_HD void transpose32(Ctx& c, double (&re)[32], double (&im)[32]) {
     const int t = c.lane();
-    double* buf = c.xbuf();
+    double* br = c.xbuf();
+    double* bi = br + kXbufDoubles;
 #pragma unroll
-    for (int r = 0; r < 32; r++) buf[r * kXPad + t] = v[r];
+    for (int r = 0; r < 32; r++) { br[r * kXPad + t] = re[r]; bi[r * kXPad + t] = im[r]; }
     c.syncwarp();
 #pragma unroll
-    for (int r = 0; r < 32; r++) v[r] = buf[t * kXPad + r];
+    for (int r = 0; r < 32; r++) { re[r] = br[t * kXPad + r]; im[r] = bi[t * kXPad + r]; }
     c.syncwarp();
 }
 
@@ -120,8 +123,7 @@ FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
         const cplx z = cmul(cplx{re[k1], im[k1]}, w);
         re[k1] = z.x; im[k1] = z.y;
     }
-    transpose32(c, re);
-    transpose32(c, im);
+    transpose32(c, re, im);
     fft32_fwd_p2(re, im);
 }
 
@@ -136,8 +138,7 @@ FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
         const cplx z = cmul(cplx{re[n2], im[n2]}, w);
         re[n2] = z.x; im[n2] = z.y;
     }
-    transpose32(c, re);
-    transpose32(c, im);
+    transpose32(c, re, im);
     fft32_inv_p2(re, im);
 }
 
@@ -165,30 +166,25 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     }
     forward1024(c, re, im, tf);
     // Fourier-domain GGSW product; the partner warp receives our contribution to ITS output
-    // polynomial, 16 spectrum rows at a time, through our transpose buffer
+    // polynomial through our transpose buffers (1024 complex points fit in the two matrices)
     cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
     const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int k2 = half * 16 + q;
-            const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
-            const cplx go = c.ldg(g + bsk_index(p, k2, 1 - p, t));
-            const cplx d = cplx{re[k2], im[k2]};
-            xo[q * 32 + t] = cmul(d, go);
-            const cplx s = cmul(d, gs);
-            re[k2] = s.x; im[k2] = s.y;
-        }
-        c.pair_sync();
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int k2 = half * 16 + q;
-            const cplx v = xp[q * 32 + t];
-            re[k2] += v.x; im[k2] += v.y;
-        }
-        c.pair_sync();
+    for (int k2 = 0; k2 < 32; k2++) {
+        const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
+        const cplx go = c.ldg(g + bsk_index(p, k2, 1 - p, t));
+        const cplx d = cplx{re[k2], im[k2]};
+        xo[k2 * 32 + t] = cmul(d, go);
+        const cplx s = cmul(d, gs);
+        re[k2] = s.x; im[k2] = s.y;
     }
+    c.pair_sync();
+#pragma unroll
+    for (int k2 = 0; k2 < 32; k2++) {
+        const cplx v = xp[k2 * 32 + t];
+        re[k2] += v.x; im[k2] += v.y;
+    }
+    c.pair_sync();
     inverse1024(c, re, im, ti);
     // accumulate into the torus accumulator; keep the new words in registers for the next step
 #pragma unroll

@@ -29,6 +29,9 @@ struct fhestr_engine {
     u64* ksk_corr = nullptr;
     cplx* tf = nullptr;
     cplx* ti = nullptr;
+    cplx* bsk_q = nullptr;     // the four-warp kernel's layout of the same key
+    cplx* qtab = nullptr;      // tq [1024] | tqt [1024] | w64 [64]
+    QuadTables qt{};
     bool keys_loaded = false;
     u64* luts = nullptr;
     int n_luts = 0, cap_luts = 256;
@@ -186,6 +189,15 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
         CKC(cudaMemcpy(e->tf, tf.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
     }
+    CKC(cudaMalloc(&e->qtab, (1024 + 1024 + 64) * sizeof(cplx)));
+    {
+        std::vector<cplx> t(1024 + 1024 + 64);
+        make_quad_tables(t.data(), t.data() + 1024, t.data() + 2048);
+        CKC(cudaMemcpy(e->qtab, t.data(), t.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+        e->qt = QuadTables{e->qtab, e->qtab + 1024, e->qtab + 2048};
+    }
+    CKC(cudaMalloc(&e->bsk_q, (size_t)p->n * kQBskStepElems * sizeof(cplx)));
+    CKC(blind_rotate_quad_configure());
     CKC(cudaMalloc(&e->luts, (size_t)e->cap_luts * kN * sizeof(u64)));
     CKC(cudaMalloc(&e->bsk_f, (size_t)p->n * kBskStepElems * sizeof(cplx)));
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
@@ -205,6 +217,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (e->comm) fhestr_comm_destroy(e);
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
+    cudaFree(e->bsk_q); cudaFree(e->qtab);
     cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -235,6 +248,7 @@ int fhestr_load_keys(fhestr_engine* e, const uint64_t* bsk_std, const uint64_t* 
     CK(cudaMemcpyAsync(d_std, bsk_std, bsk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->ksk, ksk, ksk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
     e->launches += launch_bsk_convert(d_std, p.n, e->tf, e->bsk_f, e->stream);
+    e->launches += launch_bsk_convert_quad(d_std, p.n, e->qt, e->bsk_q, e->stream);
     e->launches += launch_ksk_correction(e->ksk, kN * p.ks_level, p.n, p.ks_base_log, e->ksk_corr, e->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -330,7 +344,8 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
         br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
-        e->launches += launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+        br.bsk_q = e->bsk_q; br.qt = e->qt;
+        e->launches += e->pbs_per_cta == 8 ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
         if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
@@ -539,7 +554,8 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
     br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = d_ids; br.jobs = nullptr; br.arena = e->arena;
     br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.init_acc = d_init; br.out_acc = d_out;
     br.n = e->prm.n; br.B = (int)count;
-    e->launches += launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+    br.bsk_q = e->bsk_q; br.qt = e->qt;
+    e->launches += e->pbs_per_cta == 8 ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc_out_host, d_out, acc_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -612,7 +628,7 @@ int fhestr_get_timing(fhestr_engine* e, double* ks_ms, double* br_ms, uint64_t* 
 }
 
 int fhestr_set_pbs_per_cta(fhestr_engine* e, int v) {
-    if (!e || (v != 0 && v != 1 && v != 2 && v != 4)) return FHESTR_E_INVALID;
+    if (!e || (v != 0 && v != 1 && v != 2 && v != 4 && v != 8)) return FHESTR_E_INVALID;
     e->pbs_per_cta = v;
     return FHESTR_OK;
 }

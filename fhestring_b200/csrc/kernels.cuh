@@ -5,6 +5,7 @@
 
 #include "../../include/fhestr_engine.h"
 #include "br_core.cuh"
+#include "br_quad.cuh"
 
 namespace fhestr {
 
@@ -19,6 +20,8 @@ struct BrBatchArgs {
     const cplx* ti;
     const u64* init_acc;      // optional [B][2][N]
     u64* out_acc;             // optional [B][2][N]
+    const cplx* bsk_q;        // Fourier BSK, layout of the four-warp kernel (br_quad.cuh)
+    QuadTables qt;
     int n;
     int B;
 };
@@ -37,6 +40,10 @@ int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s);
 // K2+K3+K4: mod-switch + blind rotation + sample extract.  pbs_per_cta in {0 (auto), 1, 2, 4}.
 int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s);
 cudaError_t blind_rotate_configure();
+// the same, four warps per PBS (br_quad.cuh)
+int launch_blind_rotate_quad(const BrBatchArgs& a, cudaStream_t s);
+cudaError_t blind_rotate_quad_configure();
+int launch_bsk_convert_quad(const u64* bsk_std, int n, const QuadTables& tb, cplx* out, cudaStream_t s);
 cudaError_t keyswitch_configure();  // opt in to the large dynamic shared memory carve-out
 // leveled jobs (lut < 0): dst = sum coeff*src + constant*e_body
 int launch_linear(const fhestr_job* jobs, int B, u64* arena, cudaStream_t s);

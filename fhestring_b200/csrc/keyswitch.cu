@@ -49,11 +49,16 @@ __device__ __forceinline__ u64 job_lincomb(const fhestr_job& j, const u64* arena
     return x;
 }
 
-template <int L>
+// SPLIT = false: one CTA walks all N mask rows of its 8 ciphertexts and stores the result.
+// SPLIT = true : blockIdx.y selects one of gridDim.y row ranges; partial sums are combined with 64-bit atomic
+//                adds into a zeroed ks_out (wrapping adds commute: bit-identical to the unsplit kernel).  Used for
+//                small dependency levels, where a single CTA per 8 ciphertexts would stream the whole 58 MiB key
+//                through one SM at L2 latency (measured 4.4-5.1 ms for any batch below 2368).
+template <int L, bool SPLIT>
 __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* dig = reinterpret_cast<uint32_t*>(smem);                  // [i][BT] packed digits
-    u64* body = reinterpret_cast<u64*>(smem + (size_t)kN * kKsBT * 4);  // [BT]
+    u64* body = reinterpret_cast<u64*>(smem + (size_t)(SPLIT ? kN / (int)gridDim.y : kN) * kKsBT * 4);  // [BT]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kKsBT;
     const int nb = min(kKsBT, A.B - b0);
@@ -61,15 +66,17 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
     const int fw = A.base_log + 1;
     const uint32_t fmask = (1u << fw) - 1;
 
+    const int rows = SPLIT ? kN / (int)gridDim.y : kN;       // mask rows handled by this CTA
+    const int row0 = SPLIT ? (int)blockIdx.y * rows : 0;
     // phase 1: digits of the (never materialised) linear combination
-    for (int idx = tid; idx < kN * kKsBT; idx += kKsThreads) {
-        const int b = idx / kN, i = idx - b * kN;
+    for (int idx = tid; idx < rows * kKsBT; idx += kKsThreads) {
+        const int b = idx / rows, i = row0 + idx - b * rows;
         uint32_t packed = 0;
         if (b < nb) packed = pack_digits(job_lincomb(A.jobs[b0 + b], A.arena, i), A.base_log, level);
         else {  // neutral digits (value 0) for the padding rows
             for (int l = 0; l < level; l++) packed |= (1u << (A.base_log - 1)) << (fw * l);
         }
-        dig[i * kKsBT + b] = packed;
+        dig[(i - row0) * kKsBT + b] = packed;
     }
     if (tid < kKsBT) {
         u64 v = 0;
@@ -97,9 +104,9 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
 #pragma unroll
         for (int c = 0; c < kKsCols; c++) acc[b][c] = 0;
 
-    const u64* krow = A.ksk;
+    const u64* krow = A.ksk + (size_t)row0 * level * ncol;
 #pragma unroll 1
-    for (int i = 0; i < kN; i++) {
+    for (int i = 0; i < rows; i++) {
         uint32_t d[kKsBT];
         const uint4 d0 = *reinterpret_cast<const uint4*>(dig + i * kKsBT);
         const uint4 d1 = *reinterpret_cast<const uint4*>(dig + i * kKsBT + 4);
@@ -128,7 +135,11 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
         for (int b = 0; b < kKsBT; b++) {
             if (b >= nb) continue;
             const u64 init = (col[c] == A.n) ? body[b] : 0ull;
-            A.ks_out[(size_t)(b0 + b) * ncol + col[c]] = init - acc[b][c] + corr;
+            if (!SPLIT) A.ks_out[(size_t)(b0 + b) * ncol + col[c]] = init - acc[b][c] + corr;
+            else {
+                const u64 part = (blockIdx.y == 0 ? init + corr : 0ull) - acc[b][c];
+                atomicAdd(reinterpret_cast<unsigned long long*>(A.ks_out + (size_t)(b0 + b) * ncol + col[c]), part);
+            }
         }
     }
 }
@@ -136,18 +147,30 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatchArgs A) {
 constexpr size_t kKsSmemBytes = (size_t)kN * kKsBT * 4 + kKsBT * 8;
 
 cudaError_t keyswitch_configure() {
-    cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(keyswitch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(keyswitch_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(keyswitch_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(keyswitch_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(keyswitch_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKsSmemBytes);
 }
 
 int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s) {
     if (a.B <= 0) return 0;
     const int grid = (a.B + kKsBT - 1) / kKsBT;
-    const size_t smem = kKsSmemBytes;
-    if (a.level == 5) keyswitch_kernel<5><<<grid, kKsThreads, smem, s>>>(a);
-    else keyswitch_kernel<0><<<grid, kKsThreads, smem, s>>>(a);
-    return 1;
+    // row splits: keep about 4 CTAs per SM in flight when the level is small (powers of two up to 64)
+    int split = 1;
+    while (split < 64 && grid * split * 2 <= 148 * 4) split *= 2;
+    if (split == 1) {
+        if (a.level == 5) keyswitch_kernel<5, false><<<grid, kKsThreads, kKsSmemBytes, s>>>(a);
+        else keyswitch_kernel<0, false><<<grid, kKsThreads, kKsSmemBytes, s>>>(a);
+        return 1;
+    }
+    cudaMemsetAsync(a.ks_out, 0, (size_t)a.B * (a.n + 1) * sizeof(u64), s);
+    const dim3 g(grid, split);
+    const size_t smem = (size_t)(kN / split) * kKsBT * 4 + kKsBT * 8;
+    if (a.level == 5) keyswitch_kernel<5, true><<<g, kKsThreads, smem, s>>>(a);
+    else keyswitch_kernel<0, true><<<g, kKsThreads, smem, s>>>(a);
+    return 2;
 }
 
 // corr[c] = 2^(base_log-1) * sum_rows ksk[row][c]

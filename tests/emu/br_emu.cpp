@@ -36,7 +36,7 @@ extern "C" {
 void emu_convert_bsk(int n, const u64* bsk_std, double* out) {
     std::vector<cplx> tf(1024), ti(1024);
     make_twiddles(tf.data(), ti.data());
-    std::vector<double> xbuf(kXbufDoubles);
+    std::vector<double> xbuf(kWarpXbufDoubles);
     std::barrier<> wb(32);
     std::vector<std::thread> th;
     for (int lane = 0; lane < 32; lane++)
@@ -58,7 +58,7 @@ void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc,
     std::vector<cplx> tf(1024), ti(1024);
     make_twiddles(tf.data(), ti.data());
     std::vector<acc_t> acc(2 * kN);
-    std::vector<double> xbuf(2 * kXbufDoubles);
+    std::vector<double> xbuf(2 * kWarpXbufDoubles);
     std::vector<uint16_t> at(n + 64);
     std::barrier<> wb0(32), wb1(32), pb(64);
     BrJobView job{ks, lut, init_acc, out_lwe, out_acc, n};
@@ -66,8 +66,8 @@ void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc,
     for (int w = 0; w < 2; w++)
         for (int lane = 0; lane < 32; lane++)
             th.emplace_back([&, w, lane] {
-                HostCtx c{lane, w, acc.data() + w * kN, xbuf.data() + w * kXbufDoubles,
-                          xbuf.data() + (1 - w) * kXbufDoubles, at.data(), w ? &wb1 : &wb0, &pb};
+                HostCtx c{lane, w, acc.data() + w * kN, xbuf.data() + w * kWarpXbufDoubles,
+                          xbuf.data() + (1 - w) * kWarpXbufDoubles, at.data(), w ? &wb1 : &wb0, &pb};
                 br_thread_main(c, job, reinterpret_cast<const cplx*>(bsk_f), tf.data(), ti.data());
             });
     for (auto& t : th) t.join();

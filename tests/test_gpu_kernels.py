@@ -126,7 +126,7 @@ def test_single_external_product_tolerance(build_lib, small_oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("pbs_per_cta", [0, 1, 2, 4])
+@pytest.mark.parametrize("pbs_per_cta", [0, 1, 2, 4, 8])
 def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, pbs_per_cta):
     """K0..K4 end to end on 32 block values incl. the padding-bit half (negacyclic sign), several LUTs,
     batch size not a multiple of the CTA tile, every launch shape"""
