@@ -355,17 +355,27 @@ Char Graph::flip(const Char& a) { return sub(trivial_char(1), a); }
 // ---- wide reductions (plaintext-identical to chains of bitand / bitor / add on 0/1 chars)
 static const int kChunk = 15;
 
+// chunk sizes of a balanced reduction tree with fan-in <= kChunk: n inputs in ceil(n / kChunk) nearly equal chunks
+static std::vector<size_t> balanced_chunks(size_t n) {
+    const size_t c = (n + kChunk - 1) / kChunk;
+    std::vector<size_t> sizes(c, n / c);
+    for (size_t i = 0; i < n % c; i++) sizes[i]++;
+    return sizes;
+}
+
 Char Graph::and_all(const std::vector<Char>& flags) {
     std::vector<BlockId> cur;
     for (auto& c : flags) cur.push_back(cond_bit(c));
     if (cur.empty()) return trivial_char(1);
     while (cur.size() > 1) {
         std::vector<BlockId> nxt;
-        for (size_t i = 0; i < cur.size(); i += kChunk) {
-            const size_t k = std::min<size_t>(kChunk, cur.size() - i);
+        size_t i = 0;
+        for (size_t k : balanced_chunks(cur.size())) {
+            if (k == 1) { nxt.push_back(cur[i++]); continue; }
             std::vector<std::pair<BlockId, int>> ops;
             for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
             nxt.push_back(pbs(ops, 0, table_of([k](int v) { return v == (int)k; })));
+            i += k;
         }
         cur.swap(nxt);
     }
@@ -378,11 +388,13 @@ Char Graph::or_all(const std::vector<Char>& flags) {
     if (cur.empty()) return trivial_char(0);
     while (cur.size() > 1) {
         std::vector<BlockId> nxt;
-        for (size_t i = 0; i < cur.size(); i += kChunk) {
-            const size_t k = std::min<size_t>(kChunk, cur.size() - i);
+        size_t i = 0;
+        for (size_t k : balanced_chunks(cur.size())) {
+            if (k == 1) { nxt.push_back(cur[i++]); continue; }
             std::vector<std::pair<BlockId, int>> ops;
             for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
             nxt.push_back(pbs(ops, 0, table_of([](int v) { return v != 0; })));
+            i += k;
         }
         cur.swap(nxt);
     }
@@ -531,11 +543,21 @@ std::vector<Char> Graph::compact_nonzero(const std::vector<Char>& s) {
 
 Char Graph::nonzero(const Char& a) { return flag_char(cond_bit(a)); }
 
+// nibble-wide equality: two blocks of each char are packed lo + 4 hi and SUBTRACTED raw, exactly like the
+// reference's comparison recipe (cmp above; noise2 = 34): the difference lies in [-15, 15] and is zero iff both
+// blocks agree, so one `is zero` LUT (negative inputs carry the padding bit and return -f(.) = 0) replaces two
+// block-equality PBS.  A char equality is 2 PBS + the AND tree instead of 4.
+BlockId Graph::nibble_eq(BlockId a_lo, BlockId a_hi, BlockId b_lo, BlockId b_hi) {
+    if (a_lo == b_lo && a_hi == b_hi) return trivial_block(1);
+    SignedScope sc(signed_ok);
+    return pbs({{a_lo, 1}, {a_hi, 4}, {b_lo, -1}, {b_hi, -4}}, 0, table_of([](int v) { return v == 0; }));
+}
+
 Char Graph::block_and_eq(const std::vector<std::pair<Char, Char>>& pairs) {
     std::vector<Char> flags;
     for (auto& pr : pairs)
-        for (int i = 0; i < 4; i++)
-            flags.push_back(flag_char(bivar(pr.first[i], pr.second[i], [](int x, int y) { return x == y; })));
+        for (int h = 0; h < 2; h++)
+            flags.push_back(flag_char(nibble_eq(pr.first[2 * h], pr.first[2 * h + 1], pr.second[2 * h], pr.second[2 * h + 1])));
     return and_all(flags);
 }
 
