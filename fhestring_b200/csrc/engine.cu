@@ -27,6 +27,10 @@ struct fhestr_engine {
     cplx* bsk_f = nullptr;
     u64* ksk = nullptr;
     u64* ksk_corr = nullptr;
+    unsigned char* ksk8 = nullptr;     // limb matrix for the tensor-core keyswitch
+    unsigned char* ks_digits = nullptr;
+    u64* ks_body = nullptr;
+    int ks_path = 0;                   // 0 = tensor cores (IMMA), 1 = CUDA cores (u64 IMAD)
     cplx* tf = nullptr;
     cplx* ti = nullptr;
     cplx* bsk_q = nullptr;     // the four-warp kernel's layout of the same key
@@ -122,8 +126,13 @@ static int ensure_scratch(fhestr_engine* e, size_t n_jobs) {
     }
     if (n_jobs > e->ks_cap) {
         if (e->ks_out) CK(cudaFree(e->ks_out));
+        if (e->ks_digits) CK(cudaFree(e->ks_digits));
+        if (e->ks_body) CK(cudaFree(e->ks_body));
         e->ks_cap = n_jobs * 2 + 64;
         CK(cudaMalloc(&e->ks_out, e->ks_cap * (size_t)(e->prm.n + 1) * sizeof(u64)));
+        CK(cudaMalloc(&e->ks_digits, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level));
+        CK(cudaMemset(e->ks_digits, 0, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level));
+        CK(cudaMalloc(&e->ks_body, e->ks_cap * sizeof(u64)));
     }
     return FHESTR_OK;
 }
@@ -202,6 +211,9 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
     CKC(cudaMalloc(&e->bsk_f, (size_t)p->n * kBskStepElems * sizeof(cplx)));
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
     CKC(cudaMalloc(&e->ksk_corr, (size_t)(p->n + 1) * sizeof(u64)));
+    CKC(cudaMalloc(&e->ksk8, (size_t)ks_cols_padded(p->n) * 8 * kN * p->ks_level));
+    CKC(keyswitch_mma_configure());
+    if (p->ks_base_log > 7) e->ks_path = 1;   // unsigned digits must fit a byte
     CKC(blind_rotate_configure());
     CKC(keyswitch_configure());
     CKC(cudaStreamSynchronize(e->stream));
@@ -217,7 +229,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (e->comm) fhestr_comm_destroy(e);
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
-    cudaFree(e->bsk_q); cudaFree(e->qtab);
+    cudaFree(e->bsk_q); cudaFree(e->qtab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
     cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -250,6 +262,7 @@ int fhestr_load_keys(fhestr_engine* e, const uint64_t* bsk_std, const uint64_t* 
     e->launches += launch_bsk_convert(d_std, p.n, e->tf, e->bsk_f, e->stream);
     e->launches += launch_bsk_convert_quad(d_std, p.n, e->qt, e->bsk_q, e->stream);
     e->launches += launch_ksk_correction(e->ksk, kN * p.ks_level, p.n, p.ks_base_log, e->ksk_corr, e->stream);
+    e->launches += launch_ksk_limbs(e->ksk, kN * p.ks_level, p.n, e->ksk8, e->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaFree(d_std));
@@ -338,8 +351,8 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
             CK(cudaEventRecord(t.a, e->stream));
         }
         KsBatchArgs ks{d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_pbs,
-                       e->prm.ks_base_log, e->prm.ks_level};
-        e->launches += launch_keyswitch(ks, e->stream);
+                       e->prm.ks_base_log, e->prm.ks_level, e->ksk8, e->ks_digits, e->ks_body};
+        e->launches += e->ks_path == 0 ? launch_keyswitch_mma(ks, e->stream) : launch_keyswitch(ks, e->stream);
         if (e->timing) CK(cudaEventRecord(t.b, e->stream));
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
@@ -521,8 +534,8 @@ int fhestr_debug_keyswitch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->d_jobs, jobs, (size_t)n_jobs * sizeof(fhestr_job), cudaMemcpyHostToDevice, e->stream));
     KsBatchArgs ks{e->d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_jobs,
-                   e->prm.ks_base_log, e->prm.ks_level};
-    e->launches += launch_keyswitch(ks, e->stream);
+                   e->prm.ks_base_log, e->prm.ks_level, e->ksk8, e->ks_digits, e->ks_body};
+    e->launches += e->ks_path == 0 ? launch_keyswitch_mma(ks, e->stream) : launch_keyswitch(ks, e->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host_out, e->ks_out, (size_t)n_jobs * (e->prm.n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -624,6 +637,13 @@ int fhestr_get_timing(fhestr_engine* e, double* ks_ms, double* br_ms, uint64_t* 
     if (br_launches) *br_launches = e->timed.size();
     if (br_pbs) *br_pbs = pbs;
     drop_timed(e);
+    return FHESTR_OK;
+}
+
+int fhestr_set_keyswitch_path(fhestr_engine* e, int path) {
+    if (!e || (path != 0 && path != 1)) return FHESTR_E_INVALID;
+    if (path == 0 && e->prm.ks_base_log > 7) return fail(e, FHESTR_E_INVALID, "tensor-core keyswitch needs ks_base_log <= 7");
+    e->ks_path = path;
     return FHESTR_OK;
 }
 

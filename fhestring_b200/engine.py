@@ -149,6 +149,10 @@ class Engine:
     def set_pbs_per_cta(self, v: int):
         self._ck(self.lib.fhestr_set_pbs_per_cta(self.h, C.c_int(v)))
 
+    def set_keyswitch_path(self, path: int):
+        """0 = tensor cores (IMMA limb-split GEMM, default), 1 = CUDA cores"""
+        self._ck(self.lib.fhestr_set_keyswitch_path(self.h, C.c_int(path)))
+
     def set_timing(self, enable: bool):
         self._ck(self.lib.fhestr_set_timing(self.h, C.c_int(1 if enable else 0)))
 

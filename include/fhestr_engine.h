@@ -201,8 +201,12 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
 int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_mhz_hint);
 /* number of kernels this engine has launched so far (bench.py's gpu_launches) */
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
-/* blind-rotation launch shape override for experiments: PBS per CTA (1, 2 or 4; 0 = automatic) */
+/* blind-rotation launch shape override for experiments: PBS per CTA (1, 2 or 4; 0 = automatic); 8 selects the
+ * four-warps-per-PBS kernel (br_quad.cuh) */
 int fhestr_set_pbs_per_cta(fhestr_engine* e, int pbs_per_cta);
+/* keyswitch implementation: 0 = tensor cores (u8 limb-split IMMA GEMM, default), 1 = CUDA cores (u64 IMAD);
+ * both are exact and produce identical words */
+int fhestr_set_keyswitch_path(fhestr_engine* e, int path);
 
 /* per-kernel device timing (CUDA events on the engine stream around every keyswitch / blind-rotation
  * launch); get_timing synchronises the stream and returns the totals since the last reset */

@@ -26,8 +26,9 @@ for B in (1, 17, 148, 296, 592, 888, 1184, 2368, 4736):
     jobs = single_term_jobs(BMAX + np.arange(B), np.arange(B), ident)
     prog = eng.program(jobs, [0, B])
     row = [f"B={B:5d}"]
-    for shape in (1, 8):
-        eng.set_pbs_per_cta(shape)
+    for shape in (1, 9):
+        eng.set_pbs_per_cta(1)
+        eng.set_keyswitch_path(0 if shape == 1 else 1)
         for _ in range(2):
             prog.run()
         torch.cuda.synchronize()
@@ -41,7 +42,7 @@ for B in (1, 17, 148, 296, 592, 888, 1184, 2368, 4736):
         ks_ms, br_ms, nl, npbs = eng.get_timing()
         eng.set_timing(False)
         ok = np.array_equal(ck.decrypt_blocks(eng.download(BMAX, B)), vals[:B])
-        row.append(f"shape {shape}: level {a.elapsed_time(b) / 3:7.3f} ms (ks {ks_ms / 3:6.3f}, br {br_ms / 3:7.3f}) ok={ok}")
+        row.append(f"ks {'imma' if shape == 1 else 'imad'}: level {a.elapsed_time(b) / 3:7.3f} ms (ks {ks_ms / 3:6.3f}, br {br_ms / 3:7.3f}) ok={ok}")
     print("  ".join(row), flush=True)
     prog.close()
 eng.close()

@@ -91,6 +91,41 @@ def test_keyswitch_ragged_batches_and_linear_terms(small_engine, small_oracle, c
     assert np.array_equal(small_engine.debug_keyswitch(jobs), o.keyswitch(keys, lin))
 
 
+@pytest.mark.parametrize("count", [1, 9, 127, 128, 129, 300])
+def test_keyswitch_tensor_core_and_cuda_core_paths_identical(full_engine, full_oracle, count):
+    """K1 as an IMMA limb-split GEMM (default) and as the u64 IMAD kernel: same words, at the real parameters,
+    around the 128-row GEMM tile; and both equal the oracle on a few rows"""
+    from fhestring_b200.engine import make_jobs
+    o, keys = full_oracle
+    rng = np.random.default_rng(count)
+    cts = o.encrypt_big(keys, rng.integers(0, 16, 32), seed=100 + count)
+    full_engine.upload(0, cts)
+    jobs = make_jobs(count)
+    lid = full_engine.lut(list(range(16)))
+    for i in range(count):
+        nt = 1 + i % 3
+        jobs[i]["dst"] = 4000 + i
+        jobs[i]["lut"] = lid
+        jobs[i]["n_terms"] = nt
+        for t in range(nt):
+            jobs[i]["src"][t] = int(rng.integers(0, 32))
+            jobs[i]["coeff"][t] = int(rng.integers(-4, 5)) or 1
+        jobs[i]["constant"] = int(rng.integers(0, 16)) << 59
+    full_engine.set_keyswitch_path(0)
+    a = full_engine.debug_keyswitch(jobs)
+    full_engine.set_keyswitch_path(1)
+    b = full_engine.debug_keyswitch(jobs)
+    full_engine.set_keyswitch_path(0)
+    assert np.array_equal(a, b)
+    lin = np.zeros((min(count, 4), o.big), np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(len(lin)):
+            for t in range(int(jobs[i]["n_terms"])):
+                lin[i] += cts[int(jobs[i]["src"][t])] * np.uint64(int(jobs[i]["coeff"][t]) % 2**64)
+            lin[i, -1] += np.uint64(int(jobs[i]["constant"]))
+    assert np.array_equal(a[:len(lin)], o.keyswitch(keys, lin))
+
+
 def test_single_external_product_tolerance(build_lib, small_oracle):
     """K3 on one CMUX step with a random (worst-case, full-range) GLWE, vs exact integers + golden"""
     from fhestring_b200.engine import Engine
