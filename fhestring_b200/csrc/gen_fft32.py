@@ -42,8 +42,20 @@ class Prog:
         return name
 
 
+CONST_POOL = []   # distinct |twiddle| values; referenced as FFTC(i) so that DFMA reads them from the constant bank
+
+
 def lit(x):
-    return repr(float(x))
+    """literal for a twiddle: pooled by absolute value (values closer than 4e-16 are the same twiddle), sign kept"""
+    x = float(x)
+    if x in (0.0, 1.0, -1.0, 2.0, -2.0):
+        return repr(x)
+    a = abs(x)
+    for i, c in enumerate(CONST_POOL):
+        if abs(c - a) < 4e-16:
+            return ("-" if x < 0 else "") + f"FFTC({i})"
+    CONST_POOL.append(a)
+    return ("-" if x < 0 else "") + f"FFTC({len(CONST_POOL) - 1})"
 
 
 def emit_network(prog, re, im, rho_angle):
@@ -145,7 +157,7 @@ def simulate(prog, final, x):
         def sub(m):
             return repr(float(env[m.group(0)]))
         e = _re.sub(r"re\[\d+\]|im\[\d+\]|t\d+", sub, expr)
-        return eval(e, {"fma": lambda a, b, c: a * b + c})
+        return eval(e, {"fma": lambda a, b, c: a * b + c, "FFTC": lambda i: CONST_POOL[i]})
 
     for n, e in prog.lines:
         env[n] = ev(e)
@@ -193,8 +205,19 @@ def main():
         "#endif",
         "#include <math.h>",
         "namespace fhestr {",
+        "// twiddle constants: in the constant bank on the device (DFMA takes c[bank][offset] operands directly; as",
+        "// literals every use cost two UMOVs), a plain table on the host",
+        "#ifdef __CUDACC__",
+        "static __constant__ double kFft32ConstDev[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
+        "#endif",
+        "static const double kFft32ConstHost[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
+        "#ifdef __CUDA_ARCH__",
+        "#define FFTC(i) kFft32ConstDev[i]",
+        "#else",
+        "#define FFTC(i) kFft32ConstHost[i]",
+        "#endif",
     ]
-    out = "\n".join(hdr) + "\n\n" + "\n\n".join(funcs) + "\n\n} // namespace fhestr\n"
+    out = "\n".join(hdr) + "\n\n" + "\n\n".join(funcs) + "\n\n#undef FFTC\n} // namespace fhestr\n"
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fft32_gen.cuh")
     with open(path, "w") as f:
         f.write(out)
