@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfhestr_engine.so")
+LIB_PATH = os.environ.get("FHESTR_ENGINE_LIB") or os.path.join(_HERE, "libfhestr_engine.so")  # override: A/B runs of two builds
 MAX_TERMS = 16
 
 

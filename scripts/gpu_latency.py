@@ -22,11 +22,11 @@ eng.load_keys(bsk, ksk)
 vals = np.random.default_rng(0).integers(0, 16, BMAX).astype(np.uint8)
 eng.upload(0, ck.encrypt_blocks(vals))
 ident = eng.lut(list(range(16)))
-for B in (1, 17, 148, 296, 592, 888, 1184, 2368, 4736):
+for B in ([int(x) for x in sys.argv[1:]] or (1, 17, 148, 296, 592, 888, 1184, 2368, 4736)):
     jobs = single_term_jobs(BMAX + np.arange(B), np.arange(B), ident)
     prog = eng.program(jobs, [0, B])
     row = [f"B={B:5d}"]
-    for shape in (1, 9):
+    for shape in (1,) if len(sys.argv) > 1 else (1, 9):
         eng.set_pbs_per_cta(1)
         eng.set_keyswitch_path(0 if shape == 1 else 1)
         for _ in range(2):
