@@ -177,6 +177,57 @@ def contains_leg(eng, ck, stream, rank, world, steps, barrier):
                      "verified": bool(got == want), "h2d_bytes": int(n_in * eng.big * 8), "d2h_bytes": int(4 * eng.big * 8)}
         prog.close()
         g.close()
+    # throughput form of the same workload: Q independent queries recorded in ONE graph -- their levels merge, so
+    # every level is Q times wider and fills all ranks (the single query above is bounded by 6 PBS latencies)
+    Q = 16
+    g = Graph()
+    outs = []
+    rngq = np.random.default_rng(44)
+    bodies = []
+    for qi in range(Q):
+        b = rngq.choice(list(b"abcdefghilmnoprstu"), 256).astype(np.uint8)
+        if qi % 2 == 0:
+            b[(7 * qi) % 248:(7 * qi) % 248 + 8] = pat
+        bodies.append(np.concatenate([b, np.zeros(1, np.uint8)]))
+    ids_p, slots_p = g.input_chars(len(pat))
+    first_slot = int(slots_p[0, 0])
+    all_vals = [pat]
+    for qi in range(Q):
+        ids_s, slots_s = g.input_chars(len(bodies[qi]))
+        all_vals.append(bodies[qi])
+        _, cid = g.string_op("contains", [ids_s, ids_p], fast=True)
+        outs.append(cid)
+    g.mark_output(outs)
+    info = g.compile(world)
+    if info.slots_used <= eng.arena_blocks:
+        ctsq = ck.encrypt_u8(np.concatenate(all_vals)).reshape(-1, eng.big)
+        eng.upload(first_slot, ctsq)
+        prog = g.bind(eng)
+        for _ in range(2):
+            prog.run(rank=rank, world=world)
+        barrier()
+        times = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record(stream)
+            prog.run(rank=rank, world=world)
+            b.record(stream)
+            barrier()
+            times.append(a.elapsed_time(b))
+        t = torch.tensor([float(np.median(times))], device="cuda", dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res_slots = g.char_slots(outs)[:, 0]
+        got = [int(ck.decrypt_blocks(eng.download(int(sl), 1))[0]) for sl in res_slots]
+        want = [1 if qi % 2 == 0 else 0 for qi in range(Q)]
+        _, _, npbs, _ = g.program()
+        out["contains_x16"] = {"queries": Q, "ms": float(t[0]), "queries_per_s": Q / (float(t[0]) * 1e-3),
+                               "pbs": int(info.n_pbs), "levels": int(info.n_levels), "level_pbs": [int(x) for x in npbs],
+                               "pbs_per_s": int(info.n_pbs) / (float(t[0]) * 1e-3), "verified": bool(got == want)}
+        prog.close()
+    g.close()
     out["workload"] = ("contains/find, encrypted 8-char pattern over a 256-char encrypted string (+1 NUL padding), "
                        "depth-minimised graph, levels sharded over the ranks, NCCL all-gather per level")
     out["reference_graph"] = {"contains_pbs_nominal": 19000, "contains_levels": 260, "source": "SURVEY.md 2.6"}
@@ -250,7 +301,7 @@ def main():
     # ---- setup (untimed): keys, ciphertexts, engine
     ck = ClientKey(seed=1)
     bsk, ksk = ck.server_keys()
-    eng = Engine(arena_blocks=max(2 * B + 8, 1 << 15), device=local)
+    eng = Engine(arena_blocks=max(2 * B + 8, 1 << 17), device=local)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
