@@ -7,6 +7,9 @@
 Workload (BASELINE.json configs[1]): 4096 independent 2-bit-message radix blocks per GPU, identity LUT on
 even jobs and the bivariate-eq LUT on odd jobs, PARAM_MESSAGE_2_CARRY_2_KS_PBS (n=742, N=2048).  One step =
 one pass of the hot path (keyswitch -> mod-switch -> blind rotation -> sample extract) over the batch.
+A second leg (contains_256) measures the other half of the BASELINE metric: contains()/find() latency on a
+256-char encrypted string with an encrypted 8-char pattern (config 4), levels sharded over the ranks, plus the
+same workload batched 16 queries wide.
 Independent blocks shard across ranks with no data-path collective (weak scaling).
 
 JSON keys beyond the base contract:
