@@ -83,16 +83,14 @@ FHE_HD T rot_coef(const T* P, int j, int e) {
     return (q & kN) ? (T)0 - v : v;
 }
 
-// x in units of 2^-32 turns -> round(x) mod 2^32 (the Fourier BSK carries the 2^-32 / M scale)
+// x in units of 2^-32 turns -> round(x) mod 2^32 (the Fourier BSK carries the 2^-32 / M scale).  |x| is about
+// 2^57 (digits 2^22 x key 2^31 x sqrt(4096) terms) and the 64-bit conversion saturates only beyond 2^63, a
+// 40-sigma event, so ONE round-to-nearest conversion and a truncation replace the usual x - rint(x) sequence.
 FHE_HD acc_t torus32_from_double(double x) {
-    const double magic = 29014219670751100192948224.0;  // 1.5 * 2^84: (x + magic) - magic rounds x to a multiple of 2^32
-    const double r = (x + magic) - magic;
-    const double f = x - r;                              // exact, |f| <= 2^31
 #ifdef __CUDA_ARCH__
-    return (acc_t)__double2int_rn(f);                    // +2^31 saturates to 2^31 - 1: one ulp (2^-32), probability ~2^-20
+    return (acc_t)(unsigned long long)__double2ll_rn(x);
 #else
-    const i64 v = (i64)llrint(f);
-    return (acc_t)(int32_t)(v > 2147483647LL ? 2147483647LL : v);
+    return (acc_t)(u64)(i64)llrint(x);
 #endif
 }
 
