@@ -3,8 +3,9 @@
 //
 // Mapping: one PBS = one pair of warps (mask polynomial, body polynomial), one PBS per 64-thread CTA, 4 CTAs
 // per SM (255 registers/thread fill the 64K-register file: 8 warps, 2 per SM sub-partition).
-// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + four padded transpose
-// matrices (re / im for each warp, 4 x 8448 B) + the mod-switched mask (2 KiB) = 52 224 B.
+// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + one padded transpose
+// matrix per warp (2 x 8448 B) + the mod-switched mask (2 KiB) = 35 328 B: 4 CTAs fit the 164 KB carve-out, which
+// leaves 92 KB of L1 for the twiddle tables and the BSK tile the 4 CTAs of an SM read at nearly the same time.
 // The Fourier BSK (46 MiB for n = 742) stays resident in the 126 MB L2 and is read with 16-byte
 // read-only loads, one 64 KiB step tile per CMUX.
 #include "kernels.cuh"
@@ -13,7 +14,7 @@ namespace fhestr {
 
 constexpr int kAtildeBytes = 2048;  // up to 1024 u16
 constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
-constexpr int kPairSmemBytes = kAccBytes + 2 * kWarpXbufDoubles * 8 + kAtildeBytes;  // 52 224 B: 4 PBS per SM
+constexpr int kPairSmemBytes = kAccBytes + 2 * kWarpXbufDoubles * 8 + kAtildeBytes;  // 35 328 B
 
 struct DevCtx {
     int lane_, poly_, slot_;

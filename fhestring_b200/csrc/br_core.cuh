@@ -38,7 +38,7 @@ constexpr int kN = 2048;          // polynomial size
 constexpr int kM = 1024;          // complex points
 constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-free 64-bit column reads
 constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B: one padded 32 x 32 matrix
-constexpr int kWarpXbufDoubles = 2 * kXbufDoubles;  // per warp: one matrix for the real parts, one for the imaginary
+constexpr int kWarpXbufDoubles = kXbufDoubles;  // per warp: ONE matrix (shared-memory carve-out 164 KB instead of 228 KB: 92 KB of L1 for twiddles and the BSK tile)
 constexpr int kPbsBaseLog = 23;
 
 struct alignas(16) cplx { double x, y; };
@@ -94,19 +94,22 @@ FHE_HD acc_t torus32_from_double(double x) {
 #endif
 }
 
-// 32x32 transpose of one complex point per (lane, register) through the warp's two padded buffers: all 64
-// stores, one __syncwarp, all 64 loads -- one exposed shared-memory round trip per transform
+// 32x32 transpose of one double per (lane, register) through the warp's padded buffer, real parts then imaginary
+template <class Ctx>
+FHE_HD void transpose32_half(Ctx& c, double (&v)[32]) {
+    const int t = c.lane();
+    double* buf = c.xbuf();
+#pragma unroll
+    for (int r = 0; r < 32; r++) buf[r * kXPad + t] = v[r];
+    c.syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; r++) v[r] = buf[t * kXPad + r];
+    c.syncwarp();
+}
 template <class Ctx>
 FHE_HD void transpose32(Ctx& c, double (&re)[32], double (&im)[32]) {
-    const int t = c.lane();
-    double* br = c.xbuf();
-    double* bi = br + kXbufDoubles;
-#pragma unroll
-    for (int r = 0; r < 32; r++) { br[r * kXPad + t] = re[r]; bi[r * kXPad + t] = im[r]; }
-    c.syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; r++) { re[r] = br[t * kXPad + r]; im[r] = bi[t * kXPad + r]; }
-    c.syncwarp();
+    transpose32_half(c, re);
+    transpose32_half(c, im);
 }
 
 // forward transform of the 32 complex points held by this lane (lane = n2, register n1) into the
@@ -170,18 +173,22 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
     const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
 #pragma unroll
-    for (int k2 = 0; k2 < 32; k2++) xo[k2 * 32 + t] = cplx{re[k2], im[k2]};
-    c.pair_sync();
+    for (int half = 0; half < 2; half++) {   // 16 spectrum rows at a time: the buffer holds 528 complex points
 #pragma unroll
-    for (int k2 = 0; k2 < 32; k2++) {
-        const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
-        const cplx go = c.ldg(g + bsk_index(1 - p, k2, p, t));
-        const cplx v = xp[k2 * 32 + t];
-        const cplx s = cmul(cplx{re[k2], im[k2]}, gs);
-        re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
-        im[k2] = fma(v.x, go.y, fma(v.y, go.x, s.y));
+        for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{re[half * 16 + q], im[half * 16 + q]};
+        c.pair_sync();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int k2 = half * 16 + q;
+            const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
+            const cplx go = c.ldg(g + bsk_index(1 - p, k2, p, t));
+            const cplx v = xp[q * 32 + t];
+            const cplx s = cmul(cplx{re[k2], im[k2]}, gs);
+            re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
+            im[k2] = fma(v.x, go.y, fma(v.y, go.x, s.y));
+        }
+        c.pair_sync();
     }
-    c.pair_sync();
     inverse1024(c, re, im, ti);
     // accumulate into the torus accumulator; keep the new words in registers for the next step
 #pragma unroll
