@@ -165,6 +165,44 @@ int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_s
     return FHESTR_OK;
 }
 
+int fhestr_graph_split_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+                          uint32_t* out_chars, uint32_t out_cap, uint32_t* n_buffers, uint32_t* buffer_len,
+                          uint32_t* out_found) {
+    if (!g || (!args && n_args) || !out_chars || !n_buffers || !buffer_len || !out_found) return FHESTR_E_INVALID;
+    std::vector<Str> A(n_args);
+    for (uint32_t i = 0; i < n_args; i++) {
+        if (args[i].len && !args[i].chars) return gfail(g, FHESTR_E_INVALID, "null string argument");
+        if (!valid_ids(g, args[i].chars, args[i].len)) return gfail(g, FHESTR_E_INVALID, "char id out of range");
+        for (uint32_t j = 0; j < args[i].len; j++) A[i].push_back(g->chars[args[i].chars[j]]);
+    }
+    const bool wants_n = method == FHESTR_S_SPLITN || method == FHESTR_S_RSPLITN;
+    const uint32_t need = method == FHESTR_S_SPLIT_ASCII_WHITESPACE ? 1u : (wants_n ? 3u : 2u);
+    if (n_args != need || (wants_n && A[2].size() != 1)) return gfail(g, FHESTR_E_INVALID, "wrong arguments for this split method");
+    StringOps ops(g->g, fast != 0);
+    SplitResult r;
+    const Char two = g->g.trivial_char(2);
+    switch (method) {
+        case FHESTR_S_SPLIT: r = ops.split_impl(A[0], A[1], false, false, nullptr); break;
+        case FHESTR_S_RSPLIT: r = ops.rsplit_impl(A[0], A[1], false, false, nullptr); break;
+        case FHESTR_S_SPLIT_INCLUSIVE: r = ops.split_impl(A[0], A[1], true, false, nullptr); break;
+        case FHESTR_S_SPLIT_TERMINATOR: r = ops.split_impl(A[0], A[1], false, true, nullptr); break;
+        case FHESTR_S_RSPLIT_TERMINATOR: r = ops.rsplit_impl(A[0], A[1], false, true, nullptr); break;
+        case FHESTR_S_RSPLIT_ONCE: r = ops.rsplit_impl(A[0], A[1], false, false, &two); break;
+        case FHESTR_S_SPLITN: r = ops.split_impl(A[0], A[1], false, false, &A[2][0]); break;
+        case FHESTR_S_RSPLITN: r = ops.rsplit_impl(A[0], A[1], false, false, &A[2][0]); break;
+        case FHESTR_S_SPLIT_ASCII_WHITESPACE: r = ops.split_ascii_whitespace(A[0]); break;
+        default: return gfail(g, FHESTR_E_INVALID, "unknown split method");
+    }
+    if (!g->g.error.empty()) return gfail(g, FHESTR_E_INVALID, g->g.error);
+    *n_buffers = (uint32_t)r.buffers.size();
+    *buffer_len = r.buffers.empty() ? 0u : (uint32_t)r.buffers[0].size();
+    if ((uint64_t)*n_buffers * *buffer_len > out_cap) return gfail(g, FHESTR_E_INVALID, "split result does not fit out_cap");
+    for (size_t b = 0; b < r.buffers.size(); b++)
+        for (size_t i = 0; i < r.buffers[b].size(); i++) out_chars[b * *buffer_len + i] = push_char(g, r.buffers[b][i]);
+    *out_found = push_char(g, r.found);
+    return FHESTR_OK;
+}
+
 int fhestr_graph_mark_output(fhestr_graph* g, const uint32_t* ids, uint32_t count) {
     if (!g || (!ids && count)) return FHESTR_E_INVALID;
     if (!valid_ids(g, ids, count)) return gfail(g, FHESTR_E_INVALID, "char id out of range");

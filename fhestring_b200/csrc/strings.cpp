@@ -603,4 +603,162 @@ Str StringOps::trim_start(const Str& s) {
 
 Str StringOps::trim(const Str& s) { return trim_start(trim_end(s)); }
 
+// ------------------------------------------------------------------------------------ split.rs
+// The split family is recorded in the reference's own op order in both modes (its structure is a serial scan
+// over the string with L x L copy buffers); `fast` only selects how the inner replace / bubble_zeroes_right /
+// starts_with calls are recorded.  The graph folds what cannot change the value (trivial buffer indices,
+// untouched buffers).
+Char StringOps::rsplit_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore) {
+    Char found = one();
+    if (pattern.empty()) {
+        const Char is_pad = g.eq(s[i], zero());
+        if (i >= 1) {
+            const Char prev_non_pad = g.ne(s[i - 1], zero());
+            const Char end_of_string = g.bitand_(prev_non_pad, is_pad);
+            found = g.if_then_else(end_of_string, one(), zero());
+            found = g.bitor_(found, g.if_then_else(is_pad, zero(), one()));
+        } else {
+            found = g.if_then_else(is_pad, zero(), one());
+        }
+    } else if (pattern.size() > s.size() || i + pattern.size() >= s.size()) {
+        found = zero();
+    } else {
+        for (size_t j = 0; j < pattern.size(); j++) {
+            found = g.bitand_(found, g.eq(s[i + j], pattern[j]));
+            found = g.bitand_(found, ignore[i + j]);
+        }
+    }
+    for (size_t j = 0; j < pattern.size(); j++)
+        if (i + j < s.size()) ignore[i + j] = g.bitand_(ignore[i + j], g.if_then_else(found, zero(), one()));
+    return found;
+}
+
+Char StringOps::split_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore) {
+    Char found = one();
+    if (pattern.size() > s.size() || (long long)i < (long long)pattern.size() - 1) {
+        found = zero();
+    } else {
+        for (size_t j = 0; j < pattern.size(); j++) {
+            const size_t k = i - pattern.size() + 1 + j;
+            found = g.bitand_(found, g.eq(s[k], pattern[j]));
+            found = g.bitand_(found, ignore[k]);
+        }
+    }
+    for (size_t j = 0; j < pattern.size(); j++)
+        if (i + j < s.size()) ignore[i + j] = g.bitand_(ignore[i + j], g.if_then_else(found, zero(), one()));
+    return found;
+}
+
+void StringOps::copy_logic(size_t i, const Char* n, const Str& s, std::vector<Str>& result, const Char& allow, const Char& ccb) {
+    for (size_t j = 0; j < s.size(); j++) {
+        Char copy_flag = g.eq(g.trivial_char((uint8_t)j), ccb);
+        if (n) copy_flag = g.bitand_(copy_flag, allow);
+        result[j][i] = g.if_then_else(copy_flag, s[i], result[j][i]);
+    }
+}
+
+void StringOps::handle_n_case(const Char& found, const Char* n, Char& ccb, Char& stop) {
+    if (!n) {
+        ccb = g.if_then_else(found, g.add(ccb, one()), ccb);
+        return;
+    }
+    stop = g.bitor_(stop, g.eq(ccb, g.sub(*n, one())));
+    ccb = g.if_then_else(g.bitand_(found, g.flip(stop)), g.add(ccb, one()), ccb);
+}
+
+void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& result, const Str& pattern, bool inclusive, bool terminator) {
+    const size_t size = result.size();
+    const Str to(pattern.size(), zero());
+    if (n) {
+        Char stop_replacing = zero();
+        for (size_t i = 0; i < size; i++) {
+            stop_replacing = g.bitor_(stop_replacing, g.eq(*n, g.add(g.trivial_char((uint8_t)i), one())));
+            const Str current = bubble_zeroes_right(result[i]);
+            const Str replacement = replace(current, pattern, to);
+            for (size_t j = 0; j < size; j++) result[i][j] = g.if_then_else(stop_replacing, current[j], replacement[j]);
+        }
+        return;
+    }
+    if (!inclusive) {
+        for (size_t i = 0; i < size; i++) result[i] = replace(result[i], pattern, to);
+    } else {
+        for (size_t i = 0; i < size; i++) result[i] = bubble_zeroes_right(result[i]);
+    }
+    if (terminator) {
+        Char non_zero_found = zero();
+        for (size_t ii = 0; ii < size; ii++) {
+            const size_t i = size - 1 - ii;
+            Char is_buff_zero = one();
+            for (size_t j = 0; j < size; j++) is_buff_zero = g.bitand_(is_buff_zero, g.eq(result[i][j], zero()));
+            const Char sw = starts_with(result[i], pattern);
+            const Char should_delete = g.bitand_(g.bitand_(sw, is_buff_zero), g.flip(non_zero_found));
+            for (size_t j = 0; j < size; j++) result[i][j] = g.if_then_else(should_delete, zero(), result[i][j]);
+            non_zero_found = g.bitor_(non_zero_found, g.flip(is_buff_zero));
+        }
+    }
+}
+
+SplitResult StringOps::rsplit_impl(const Str& s_in, const Str& pattern, bool inclusive, bool terminator, const Char* n) {
+    Str s = s_in;
+    s.push_back(zero());
+    const size_t size = s.size();
+    Char ccb = zero(), stop = zero(), found_any = zero();
+    std::vector<Str> result(size, Str(size, zero()));
+    const Char allow = n ? g.ne(*n, zero()) : zero();
+    Str ignore(size, one());
+    for (size_t ii = 0; ii < size; ii++) {
+        const size_t i = size - 1 - ii;
+        copy_logic(i, n, s, result, allow, ccb);
+        const Char found = rsplit_pattern_matching(i, s, pattern, ignore);
+        found_any = g.bitor_(found_any, found);
+        handle_n_case(found, n, ccb, stop);
+    }
+    clear_pattern_from_result(n, result, pattern, inclusive, terminator);
+    return SplitResult{result, found_any};
+}
+
+SplitResult StringOps::split_impl(const Str& s_in, const Str& pattern, bool inclusive, bool terminator, const Char* n) {
+    Str s = s_in;
+    s.push_back(zero());
+    const size_t size = s.size();
+    Char ccb = zero(), stop = zero(), found_any = zero();
+    std::vector<Str> result(size, Str(size, zero()));
+    const Char allow = n ? g.ne(*n, zero()) : zero();
+    Str ignore(size, one());
+    if (pattern.empty() && n) {
+        const Char skip_first = g.bitand_(g.gt(*n, one()), g.le(*n, len(s)));
+        ccb = g.if_then_else(skip_first, one(), ccb);
+    }
+    for (size_t i = 0; i < size; i++) {
+        copy_logic(i, n, s, result, allow, ccb);
+        const Char found = split_pattern_matching(i, s, pattern, ignore);
+        found_any = g.bitor_(found_any, found);
+        handle_n_case(found, n, ccb, stop);
+    }
+    clear_pattern_from_result(n, result, pattern, inclusive, terminator);
+    return SplitResult{result, found_any};
+}
+
+SplitResult StringOps::split_ascii_whitespace(const Str& s) {
+    const size_t size = s.size();
+    Char ccb = zero(), prev_ws = one(), found_any = zero();
+    std::vector<Str> result(size, Str(size, zero()));
+    for (size_t i = 0; i < size; i++) {
+        const Char found = g.is_whitespace(s[i]);
+        found_any = g.bitor_(found_any, found);
+        ccb = g.if_then_else(g.bitand_(found, g.flip(prev_ws)), g.add(ccb, one()), ccb);
+        const Char not_ws = g.flip(g.is_whitespace(s[i]));
+        for (size_t j = 0; j < size; j++) {
+            const Char copy_flag = g.bitand_(g.eq(g.trivial_char((uint8_t)j), ccb), not_ws);
+            result[j][i] = g.if_then_else(copy_flag, s[i], result[j][i]);
+        }
+        prev_ws = found;
+    }
+    for (size_t j = 0; j < size; j++)
+        for (size_t k = 0; k < size; k++)
+            result[j][k] = g.if_then_else(g.is_whitespace(result[j][k]), zero(), result[j][k]);
+    for (size_t j = 0; j < size; j++) result[j] = bubble_zeroes_right(result[j]);
+    return SplitResult{result, found_any};
+}
+
 }  // namespace fhestr

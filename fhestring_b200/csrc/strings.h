@@ -23,6 +23,11 @@ struct StripResult {
     Char found;
 };
 
+struct SplitResult {           // FheSplit (/root/reference/src/ciphertext/fhesplit.rs:5-8)
+    std::vector<Str> buffers;  // max_no_buffers padded strings of equal length
+    Char found;
+};
+
 class StringOps {
 public:
     StringOps(Graph& graph, bool fast_mode) : g(graph), fast(fast_mode) {}
@@ -51,6 +56,10 @@ public:
     Str trim_end(const Str& s);                                             // trim.rs:36
     Str trim_start(const Str& s);                                           // trim.rs:86
     Str trim(const Str& s);                                                 // trim.rs:146
+    // split family (/root/reference/src/server_key/split.rs); n == nullptr is the reference's Option::None
+    SplitResult rsplit_impl(const Str& s, const Str& pattern, bool inclusive, bool terminator, const Char* n);  // :307
+    SplitResult split_impl(const Str& s, const Str& pattern, bool inclusive, bool terminator, const Char* n);   // :883
+    SplitResult split_ascii_whitespace(const Str& s);                                                          // :1377
 
     std::string error;  // set when a method hits one of the reference's panics
 
@@ -65,6 +74,11 @@ private:
     Str handle_shorter_from(const Str& bytes, const Str& from, const Str& to, const Char& n, bool use_counter);
     std::vector<Char> last_one_hot(const std::vector<Char>& flags, Char* any);
     Char is_not_blank(const Char& c);
+    Char rsplit_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);   // split.rs:10
+    Char split_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);    // split.rs:70
+    void copy_logic(size_t i, const Char* n, const Str& s, std::vector<Str>& result, const Char& allow, const Char& ccb);  // :108
+    void handle_n_case(const Char& found, const Char* n, Char& ccb, Char& stop);              // split.rs:137
+    void clear_pattern_from_result(const Char* n, std::vector<Str>& result, const Str& pattern, bool inclusive, bool terminator);  // :180
 };
 
 }  // namespace fhestr

@@ -98,6 +98,25 @@ class FheStrip:
         return client_key.decrypt(strip.string), client_key.decrypt_char(strip.pattern_found)
 
 
+class FheSplit:
+    """fhesplit.rs:5-8"""
+
+    def __init__(self, buffers, pattern_found: FheAsciiChar):
+        self.buffers, self.pattern_found = buffers, pattern_found
+
+    @staticmethod
+    def decrypt(fhe_split: "FheSplit", client_key: "MyClientKey"):  # fhesplit.rs:29-40
+        chars = [c for b in fhe_split.buffers for c in b.bytes] + [fhe_split.pattern_found]
+        vals = client_key.decrypt_padded(chars)     # one flush + one download for the whole result
+        out, k = [], 0
+        for b in fhe_split.buffers:
+            raw = bytes(vals[k:k + len(b)])
+            k += len(b)
+            cut = raw.find(b"\0")
+            out.append((raw if cut < 0 else raw[:cut]).decode("utf-8"))
+        return out, vals[-1]
+
+
 class MyClientKey:
     """client_key.rs:9-106.  Host-side keygen / encrypt / decrypt through fhestr_client_* (seeded)."""
 
@@ -293,6 +312,32 @@ class MyServerKey:
     def trim_end(self, string, public_parameters=None): return self._str("trim_end", string)[0]            # trim.rs:36
     def trim_start(self, string, public_parameters=None): return self._str("trim_start", string)[0]        # trim.rs:86
     def trim(self, string, public_parameters=None): return self._str("trim", string)[0]                    # trim.rs:146
+
+    # ---- split family (server_key/split.rs)
+    def _split(self, method, *args):
+        ids = [self._adopt_all(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a))
+               if len(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a)) else np.zeros(0, np.uint32)
+               for a in args]
+        bufs, found = self.graph.split_op(method, ids, fast=self.fast)
+        return FheSplit([FheString([self._wrap(i) for i in row]) for row in bufs], self._wrap(found))
+
+    def split(self, string, pattern, public_parameters=None): return self._split("split", string, pattern)                        # :1038
+    def split_clear(self, string, clear_pattern, public_parameters=None): return self.split(string, self._clear(clear_pattern))      # :1094
+    def rsplit(self, string, pattern, public_parameters=None): return self._split("rsplit", string, pattern)                      # :439
+    def rsplit_clear(self, string, clear_pattern, public_parameters=None): return self.rsplit(string, self._clear(clear_pattern))    # :492
+    def split_inclusive(self, string, pattern, public_parameters=None): return self._split("split_inclusive", string, pattern)    # :1155
+    def split_inclusive_clear(self, string, clear_pattern, public_parameters=None): return self.split_inclusive(string, self._clear(clear_pattern))  # :1211
+    def split_terminator(self, string, pattern, public_parameters=None): return self._split("split_terminator", string, pattern)  # :1267
+    def split_terminator_clear(self, string, clear_pattern, public_parameters=None): return self.split_terminator(string, self._clear(clear_pattern))  # :1319
+    def rsplit_terminator(self, string, pattern, public_parameters=None): return self._split("rsplit_terminator", string, pattern)  # :806
+    def rsplit_terminator_clear(self, string, clear_pattern, public_parameters=None): return self.rsplit_terminator(string, self._clear(clear_pattern))  # :863
+    def rsplit_once(self, string, pattern, public_parameters=None): return self._split("rsplit_once", string, pattern)            # :681
+    def rsplit_once_clear(self, string, clear_pattern, public_parameters=None): return self.rsplit_once(string, self._clear(clear_pattern))  # :736
+    def splitn(self, string, pattern, n, public_parameters=None): return self._split("splitn", string, pattern, n)                # :1497
+    def splitn_clear(self, string, clear_pattern, clear_n: int, public_parameters=None): return self.splitn(string, self._clear(clear_pattern), self._trivial(clear_n))  # :1553
+    def rsplitn(self, string, pattern, n, public_parameters=None): return self._split("rsplitn", string, pattern, n)              # :553
+    def rsplitn_clear(self, string, clear_pattern, clear_n: int, public_parameters=None): return self.rsplitn(string, self._clear(clear_pattern), self._trivial(clear_n))  # :614
+    def split_ascii_whitespace(self, string, public_parameters=None): return self._split("split_ascii_whitespace", string)        # :1377
 
     def _find(self, method, string, pattern):
         from .engine import EngineError

@@ -26,6 +26,12 @@ METHODS = {
 }
 
 
+SPLIT_METHODS = {
+    "split": 0, "rsplit": 1, "split_inclusive": 2, "split_terminator": 3, "rsplit_terminator": 4, "rsplit_once": 5,
+    "splitn": 6, "rsplitn": 7, "split_ascii_whitespace": 8,
+}
+
+
 class StrArg(C.Structure):
     _fields_ = [("chars", C.POINTER(C.c_uint32)), ("len", C.c_uint32)]
 
@@ -115,6 +121,22 @@ class Graph:
         s = out[:out_len.value].copy() if kind_str else None
         ch = None if out_char.value == 0xFFFFFFFF else out_char.value
         return s, ch
+
+    def split_op(self, method: str, args, fast: bool = True):
+        """the split family (split.rs) -> (buffers as an array [n_buffers][buffer_len] of char ids, found char id)"""
+        arrs = [np.ascontiguousarray(a, np.uint32).ravel() for a in args]
+        sa = (StrArg * max(1, len(arrs)))()
+        for i, a in enumerate(arrs):
+            sa[i].chars = _u32p(a)
+            sa[i].len = len(a)
+        L = len(arrs[0]) + 2
+        cap = L * (L + 1)
+        out = np.zeros(cap, np.uint32)
+        nb, bl, found = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.fhestr_graph_split_op(self.h, C.c_int(SPLIT_METHODS[method]), C.c_int(1 if fast else 0), sa,
+                                                C.c_uint32(len(arrs)), _u32p(out), C.c_uint32(cap), C.byref(nb),
+                                                C.byref(bl), C.byref(found)))
+        return out[:nb.value * bl.value].reshape(nb.value, bl.value).copy(), found.value
 
     def mark_output(self, ids):
         a = np.ascontiguousarray(ids, np.uint32).ravel()

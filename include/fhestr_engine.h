@@ -164,6 +164,18 @@ int fhestr_graph_char_op(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32
 int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
                            uint64_t clear_n, uint32_t* out_chars, uint32_t out_cap, uint32_t* out_len,
                            uint32_t* out_char);
+enum {  /* fhestr_graph_split_op: the split family of /root/reference/src/server_key/split.rs (line) */
+    FHESTR_S_SPLIT = 0 /* :1038 */, FHESTR_S_RSPLIT = 1 /* :439 */, FHESTR_S_SPLIT_INCLUSIVE = 2 /* :1155 */,
+    FHESTR_S_SPLIT_TERMINATOR = 3 /* :1267 */, FHESTR_S_RSPLIT_TERMINATOR = 4 /* :806 */,
+    FHESTR_S_RSPLIT_ONCE = 5 /* :681 */, FHESTR_S_SPLITN = 6 /* :1497 */, FHESTR_S_RSPLITN = 7 /* :553 */,
+    FHESTR_S_SPLIT_ASCII_WHITESPACE = 8 /* :1377 */
+};
+/* args: string, pattern (not for SPLIT_ASCII_WHITESPACE), and for SPLITN / RSPLITN the encrypted n as a 1-char
+ * argument.  Result (FheSplit, fhesplit.rs:5-8): *n_buffers buffers of *buffer_len chars each, written to
+ * out_chars[b * buffer_len + i] (capacity out_cap chars), and the pattern_found flag in *out_found. */
+int fhestr_graph_split_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+                          uint32_t* out_chars, uint32_t out_cap, uint32_t* n_buffers, uint32_t* buffer_len,
+                          uint32_t* out_found);
 int fhestr_graph_mark_output(fhestr_graph* g, const uint32_t* ids, uint32_t count);
 /* levelise everything the marked outputs need; slot_align = number of ranks the levels will be sharded over */
 int fhestr_graph_compile(fhestr_graph* g, uint32_t slot_align, fhestr_graph_info* info);

@@ -389,3 +389,165 @@ def trim_start(s):  # trim.rs:86-112
 
 def trim(s):  # trim.rs:146-149
     return trim_start(trim_end(s))
+
+
+# ---------------------------------------------------------------- server_key/split.rs
+# A split result is (buffers, pattern_found): max_no_buffers = len(string) + 1 buffers (the string gets one more
+# NUL pushed, split.rs:322,898), each a padded FheString; FheSplit::decrypt (fhesplit.rs:29-40) cuts every buffer
+# at its first NUL.  The reference's tests and CLI compare trim_vector(buffers) with trim_str_vector(std result)
+# (utils.rs:59-92): empty strings are dropped at both ends.
+def _rsplit_pattern_matching(i, s, pattern, ignore):  # split.rs:10-68
+    found = 1
+    if not pattern:
+        is_pad = c_eq(s[i], 0)
+        if i >= 1:
+            prev_non_pad = c_ne(s[i - 1], 0)
+            end_of_string = c_and(prev_non_pad, is_pad)
+            found = c_ite(end_of_string, 1, 0)
+            found = c_or(found, c_ite(is_pad, 0, 1))
+        else:
+            found = c_ite(is_pad, 0, 1)
+    elif len(pattern) > len(s) or i + len(pattern) >= len(s):
+        found = 0
+    else:
+        for j, pc in enumerate(pattern):
+            found = c_and(found, c_eq(s[i + j], pc))
+            found = c_and(found, ignore[i + j])
+    for j in range(len(pattern)):
+        if i + j < len(s):
+            ignore[i + j] = c_and(ignore[i + j], c_ite(found, 0, 1))
+    return found
+
+
+def _split_pattern_matching(i, s, pattern, ignore):  # split.rs:70-106
+    found = 1
+    if len(pattern) > len(s) or i < len(pattern) - 1:
+        found = 0
+    else:
+        for j, pc in enumerate(pattern):
+            k = i - len(pattern) + 1 + j
+            found = c_and(found, c_eq(s[k], pc))
+            found = c_and(found, ignore[k])
+    for j in range(len(pattern)):
+        if i + j < len(s):
+            ignore[i + j] = c_and(ignore[i + j], c_ite(found, 0, 1))
+    return found
+
+
+def _copy_logic(i, n, s, result, allow_copying, current_copy_buffer):  # split.rs:108-135
+    for j in range(len(s)):
+        copy_flag = c_eq(j & 255, current_copy_buffer)
+        if n is not None:
+            copy_flag = c_and(copy_flag, allow_copying)
+        result[j][i] = c_ite(copy_flag, s[i], result[j][i])
+
+
+def _handle_n_case(found, n, ccb, stop):  # split.rs:137-178 -> (current_copy_buffer, stop_counter_increment)
+    if n is None:
+        return c_ite(found, c_add(ccb, 1), ccb), stop
+    stop = c_or(stop, c_eq(ccb, c_sub(n, 1)))
+    return c_ite(c_and(found, c_flip(stop)), c_add(ccb, 1), ccb), stop
+
+
+def _clear_pattern_from_result(n, result, pattern, is_inclusive, is_terminator):  # split.rs:180-305
+    size = len(result)
+    to = [0] * len(pattern)
+    if n is not None:
+        stop_replacing = 0
+        for i in range(size):
+            stop_replacing = c_or(stop_replacing, c_eq(n, c_add(i & 255, 1)))
+            current = bubble_zeroes_right(result[i])
+            replacement = replace(current, pattern, to)
+            for j in range(size):
+                result[i][j] = c_ite(stop_replacing, current[j], replacement[j])
+        return
+    if not is_inclusive:
+        for i in range(size):
+            result[i] = replace(result[i], pattern, to)
+    else:
+        for i in range(size):
+            result[i] = bubble_zeroes_right(result[i])
+    if is_terminator:
+        non_zero_found = 0
+        for i in reversed(range(size)):
+            is_buff_zero = 1
+            for j in range(size):
+                is_buff_zero = c_and(is_buff_zero, c_eq(result[i][j], 0))
+            sw = starts_with(result[i], pattern)
+            should_delete = c_and(c_and(sw, is_buff_zero), c_flip(non_zero_found))
+            for j in range(size):
+                result[i][j] = c_ite(should_delete, 0, result[i][j])
+            non_zero_found = c_or(non_zero_found, c_flip(is_buff_zero))
+
+
+def _rsplit(s, pattern, is_inclusive, is_terminator, n):  # split.rs:307-393
+    s = list(s) + [0]
+    size = len(s)
+    ccb, stop, found_any = 0, 0, 0
+    result = [[0] * size for _ in range(size)]
+    allow = c_ne(n, 0) if n is not None else 0
+    ignore = [1] * size
+    for i in reversed(range(size)):
+        _copy_logic(i, n, s, result, allow, ccb)
+        found = _rsplit_pattern_matching(i, s, pattern, ignore)
+        found_any = c_or(found_any, found)
+        ccb, stop = _handle_n_case(found, n, ccb, stop)
+    _clear_pattern_from_result(n, result, pattern, is_inclusive, is_terminator)
+    return result, found_any
+
+
+def _split(s, pattern, is_inclusive, is_terminator, n):  # split.rs:883-988
+    s = list(s) + [0]
+    size = len(s)
+    ccb, stop, found_any = 0, 0, 0
+    result = [[0] * size for _ in range(size)]
+    allow = c_ne(n, 0) if n is not None else 0
+    ignore = [1] * size
+    if not pattern and n is not None:
+        skip_first = c_and(c_gt(n, 1), c_le(n, length(s)))
+        ccb = c_ite(skip_first, 1, ccb)
+    for i in range(size):
+        _copy_logic(i, n, s, result, allow, ccb)
+        found = _split_pattern_matching(i, s, pattern, ignore)
+        found_any = c_or(found_any, found)
+        ccb, stop = _handle_n_case(found, n, ccb, stop)
+    _clear_pattern_from_result(n, result, pattern, is_inclusive, is_terminator)
+    return result, found_any
+
+
+def rsplit(s, pattern): return _rsplit(s, pattern, False, False, None)              # split.rs:439
+def rsplitn(s, pattern, n): return _rsplit(s, pattern, False, False, n)            # split.rs:553
+def rsplit_once(s, pattern): return _rsplit(s, pattern, False, False, 2)           # split.rs:681 (n = trivial 2)
+def rsplit_terminator(s, pattern): return _rsplit(s, pattern, False, True, None)   # split.rs:806
+def split(s, pattern): return _split(s, pattern, False, False, None)               # split.rs:1038
+def split_inclusive(s, pattern): return _split(s, pattern, True, False, None)      # split.rs:1155
+def split_terminator(s, pattern): return _split(s, pattern, False, True, None)     # split.rs:1267
+def splitn(s, pattern, n): return _split(s, pattern, False, False, n)              # split.rs:1497
+
+
+def split_ascii_whitespace(s):  # split.rs:1377-1447 (no extra NUL is pushed here)
+    size = len(s)
+    ccb, prev_ws, found_any = 0, 1, 0
+    result = [[0] * size for _ in range(size)]
+    for i in range(size):
+        found = c_is_whitespace(s[i])
+        found_any = c_or(found_any, found)
+        ccb = c_ite(c_and(found, c_flip(prev_ws)), c_add(ccb, 1), ccb)
+        for j in range(size):
+            copy_flag = c_and(c_eq(j & 255, ccb), c_flip(c_is_whitespace(s[i])))
+            result[j][i] = c_ite(copy_flag, s[i], result[j][i])
+        prev_ws = found
+    for j in range(size):
+        for k in range(size):
+            result[j][k] = c_ite(c_is_whitespace(result[j][k]), 0, result[j][k])
+    return [bubble_zeroes_right(b) for b in result], found_any
+
+
+def decrypt_split(res):
+    """FheSplit::decrypt (fhesplit.rs:29-40) then utils.rs:59-70 trim_vector -> (list of str, found)"""
+    bufs = [decrypt_str(b) for b in res[0]]
+    while bufs and bufs[0] == "":
+        bufs.pop(0)
+    while bufs and bufs[-1] == "":
+        bufs.pop()
+    return bufs, int(res[1])

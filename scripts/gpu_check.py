@@ -87,7 +87,7 @@ def full_checks(B=4096):
     jobs = single_term_jobs(B + np.arange(B), np.arange(B), ident)
     jobs["lut"][1::2] = eq
     tf, mhz = eng.measure_fp64_peak(); print("measured FP64 peak TFLOP/s", tf, "clock attr MHz", mhz)
-    for P in (1, 8):
+    for P in (1, 2, 4, 8):
         eng.set_pbs_per_cta(P)
         prog = eng.program(jobs, [0, B])
         for _ in range(2): prog.run()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Write reference_tests.json: the literal inputs of the reference's own unit tests
-(/root/reference/src/main.rs:138-1153, non-split methods) with the value Rust `std` gives on them --
+(/root/reference/src/main.rs:138-1153, all 43) with the value Rust `std` gives on them --
 which is what each reference test asserts against.  `std` results are spelled out with the Python
 expression that has the same meaning on these ASCII inputs; nothing here touches the oracle.
 
@@ -55,6 +55,38 @@ add("less_equal", 847, "le", ["aaa", "aaaa"], 1, int("aaa" <= "aaaa"))
 add("greater_than", 875, "gt", ["aaa", "aaaa"], 1, int("aaa" > "aaaa"))
 add("greater_equal", 903, "ge", ["aaa", "aaaa"], 1, int("aaa" >= "aaaa"))
 
+# split family (main.rs:931-1153): expected = trim_str_vector(std result) (utils.rs:72-92); the found flag is not
+# asserted by the reference tests
+def trimv(v):
+    v = list(v)
+    while v and v[0] == "":
+        v.pop(0)
+    while v and v[-1] == "":
+        v.pop()
+    return v
+
+
+def split_terminator(s, p):   # Rust: like split, but a trailing empty piece is dropped
+    parts = s.split(p)
+    return parts[:-1] if parts and parts[-1] == "" else parts
+
+
+def split_inclusive(s, p):    # Rust: pieces keep their terminator; no trailing empty piece
+    parts = s.split(p)
+    out = [x + p for x in parts[:-1]]
+    return out + ([parts[-1]] if parts[-1] else [])
+
+
+add("split", 931, "split", [" Mary had a", " "], 1, trimv(" Mary had a".split(" ")))
+add("split_inclusive", 955, "split_inclusive", ["Mary had a", " "], 1, trimv(split_inclusive("Mary had a", " ")))
+add("split_terminator", 979, "split_terminator", [".A.B.", "."], 1, trimv(split_terminator(".A.B.", ".")))
+add("split_ascii_whitespace", 1003, "split_ascii_whitespace", [" A\nB\t"], 1, trimv(" A\nB\t".split()))
+add("splitn", 1025, "splitn", [".A.B.C.", ".", 2], 1, trimv(".A.B.C.".split(".", 1)))
+add("rsplit", 1055, "rsplit", [".A.B.C.", "."], 1, trimv(".A.B.C.".split(".")[::-1]))
+add("rsplit_once", 1079, "rsplit_once", [".A.B.C.", "."], 1, trimv([".A.B.C.".rsplit(".", 1)[1], ".A.B.C.".rsplit(".", 1)[0]]))
+add("rsplitn", 1104, "rsplitn", [".A.B.C.", ".", 3], 1, trimv(".A.B.C.".rsplit(".", 2)[::-1]))
+add("rsplit_terminator", 1134, "rsplit_terminator", ["....A.B.C.", "."], 1, trimv(split_terminator("....A.B.C.", ".")[::-1]))
+
 # the CLI self-check of BASELINE config 1 (src/main.rs:47-100, src/utils.rs:122-718):
 # --string hello --pattern ello --n 1 --from ello --to _llo, STRING_PADDING = 1
 cli = dict(string="hello", pattern="ello", n=1, frm="ello", to="_llo")
@@ -85,6 +117,15 @@ CLI = [
     ("Ge", "ge", [h, p], int(h >= p)),
     ("Eq", "eq", [h, p], int(h == p)),
     ("Ne", "ne", [h, p], int(h != p)),
+    ("Rsplit", "rsplit", [h, p], trimv(h.split(p)[::-1])),
+    ("RsplitOnce", "rsplit_once", [h, p], trimv([h.rsplit(p, 1)[1], h.rsplit(p, 1)[0]])),
+    ("RsplitN", "rsplitn", [h, p, n], trimv(h.rsplit(p, n - 1)[::-1])),
+    ("RsplitTerminator", "rsplit_terminator", [h, p], trimv(split_terminator(h, p)[::-1])),
+    ("Split", "split", [h, p], trimv(h.split(p))),
+    ("SplitAsciiWhitespace", "split_ascii_whitespace", [h], trimv(h.split())),
+    ("SplitInclusive", "split_inclusive", [h, p], trimv(split_inclusive(h, p))),
+    ("SplitTerminator", "split_terminator", [h, p], trimv(split_terminator(h, p))),
+    ("SplitN", "splitn", [h, p, n], trimv(h.split(p, n - 1))),
 ]
 for nm, method, args, expect in CLI:
     add("cli_" + nm, 47, method, args, 1, expect)

@@ -21,6 +21,10 @@ SIGNATURES = {
     "lt": ("ss", "u8"), "le": ("ss", "u8"), "gt": ("ss", "u8"), "ge": ("ss", "u8"),
     "concatenate": ("ss", "str"),
     "strip_prefix": ("sp", "strip"), "strip_suffix": ("sp", "strip"),
+    # split family: result kind "split" = (list of padded buffers, found flag)
+    "split": ("sp", "split"), "rsplit": ("sp", "split"), "split_inclusive": ("sp", "split"),
+    "split_terminator": ("sp", "split"), "rsplit_terminator": ("sp", "split"), "rsplit_once": ("sp", "split"),
+    "splitn": ("spn", "split"), "rsplitn": ("spn", "split"), "split_ascii_whitespace": ("s", "split"),
 }
 
 
@@ -58,4 +62,11 @@ def decode_result(method, res):
         return int(res)
     if kind == "str":
         return cut_at_nul(res)
+    if kind == "split":   # FheSplit::decrypt + trim_vector (utils.rs:59-70); the reference's tests ignore the flag
+        bufs = [cut_at_nul(b) for b in res[0]]
+        while bufs and bufs[0] == "":
+            bufs.pop(0)
+        while bufs and bufs[-1] == "":
+            bufs.pop()
+        return bufs
     return [cut_at_nul(res[0]), int(res[1])]

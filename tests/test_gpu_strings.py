@@ -40,6 +40,14 @@ def call_method(ck, sk, pp, method, args, padding):
         else:
             enc.append(int(a))
     res = getattr(sk, method)(*enc, pp)
+    if rkind == "split":   # FheSplit: every buffer padded, plus the pattern_found flag, in one flush
+        chars = [c for b in res.buffers for c in b.bytes] + [res.pattern_found]
+        vals = ck.decrypt_padded(chars)
+        bufs, k = [], 0
+        for b in res.buffers:
+            bufs.append(vals[k:k + len(b)])
+            k += len(b)
+        return bufs, vals[-1]
     if rkind == "u8":
         return ck.decrypt_char(res)
     if rkind == "str":
@@ -64,6 +72,26 @@ def test_reference_unit_tests_fast(keys, case):
         assert list(got) == list(ref)
     elif SIGNATURES[m][1] == "u8":
         assert int(got) == int(ref)
+    elif SIGNATURES[m][1] == "split":
+        assert [list(b) for b in got[0]] == [list(b) for b in ref[0]] and int(got[1]) == int(ref[1])
+
+
+def test_split_decrypt_like_the_reference(keys):
+    """FheSplit::decrypt + trim_vector exactly as the reference's test body does (main.rs:931-953)"""
+    from fhestring_b200.fhestring import FheSplit
+    ck, sk, pp = keys
+    sk.reset()
+    my_string = ck.encrypt(" Mary had a", 1, pp, sk.key)
+    pattern = ck.encrypt_no_padding(" ")
+    plain_split, found = FheSplit.decrypt(sk.split(my_string, pattern, pp), ck)
+    while plain_split and plain_split[0] == "":
+        plain_split.pop(0)
+    while plain_split and plain_split[-1] == "":
+        plain_split.pop()
+    assert plain_split == [x for x in " Mary had a".split(" ") if x] and found == 1
+    sk.reset()
+    got, found = FheSplit.decrypt(sk.rsplitn_clear(ck.encrypt(".A.B.C.", 1, pp, sk.key), ".", 3, pp), ck)
+    assert [x for x in got if x] == ["C", ".A.B"]
 
 
 FAITHFUL = ["valid_contains", "valid_ends_with", "valid_starts_with", "lowercase", "len", "find", "eq", "less_than",

@@ -23,6 +23,8 @@ def Graph(build_lib):
 def run_method(Graph, method, enc_args, fast, slot_align=1):
     """record `method` on encrypted inputs holding enc_args, compile, interpret -> (decoded result, info)"""
     kinds, rkind = SIGNATURES[method]
+    if rkind == "split":
+        return run_split(Graph, method, enc_args, fast, slot_align)
     g = Graph()
     ids, in_slots, in_vals, clear_n = [], [], [], 0
     for kind, a in zip(kinds, enc_args):
@@ -47,6 +49,29 @@ def run_method(Graph, method, enc_args, fast, slot_align=1):
     return ([int(v) for v in res_chars[:-1]], int(res_chars[-1])), info
 
 
+def run_split(Graph, method, enc_args, fast, slot_align=1):
+    kinds, _ = SIGNATURES[method]
+    g = Graph()
+    ids, in_slots, in_vals = [], [], []
+    for kind, a in zip(kinds, enc_args):
+        vals = [a] if kind == "n" else list(a)
+        if not vals:           # empty pattern
+            ids.append(np.zeros(0, np.uint32))
+            continue
+        i, s = g.input_chars(len(vals))
+        ids.append(i)
+        in_slots.append(s.reshape(-1))
+        in_vals.append(blocks_of(vals).reshape(-1))
+    bufs, found = g.split_op(method, ids, fast=fast)
+    outs = list(bufs.reshape(-1)) + [found]
+    g.mark_output(outs)
+    info = g.compile(slot_align)
+    values = run_program(g, np.concatenate(in_slots) if in_slots else [], np.concatenate(in_vals) if in_vals else [])
+    res = chars_of(values, g.char_slots(outs))
+    nb, bl = bufs.shape
+    return ([[int(v) for v in res[b * bl:(b + 1) * bl]] for b in range(nb)], int(res[-1])), info
+
+
 def oracle_raw(method, enc_args):
     return ORACLE_FN[method](*enc_args)
 
@@ -63,6 +88,8 @@ def test_reference_cases(Graph, case, fast):
         return
     if not fast and m in ("repeat",) and len(args[0]) > 4:
         pytest.skip("16 x len chars through the O(L^2) bubble pass: covered on a shorter string below")
+    if not fast and SIGNATURES[m][1] == "split" and len(args[0]) > 7:
+        pytest.skip("L buffers through replace + the O(L^2) bubble pass each: the faithful recording is covered on the CLI inputs")
     got, _ = run_method(Graph, m, args, fast)
     assert decode_result(m, got) == case["expect"]
     # and the full padded result (not only the part before the first NUL) equals the reference algorithm's
@@ -73,6 +100,10 @@ def test_reference_cases(Graph, case, fast):
         assert int(got[1]) == int(ref[1])
         if int(ref[1]) or m == "strip_prefix":
             assert list(got[0]) == list(ref[0])
+    elif SIGNATURES[m][1] == "split":
+        # every buffer, NULs included, and the pattern_found flag equal the reference algorithm's
+        assert [list(b) for b in got[0]] == [list(b) for b in ref[0]]
+        assert int(got[1]) == int(ref[1])
 
 
 CHAR_CASES = [
@@ -128,7 +159,7 @@ def random_cases(seed, count):
     rng = random.Random(seed)
     out = []
     for _ in range(count):
-        m = rng.choice(sorted(SIGNATURES))
+        m = rng.choice(sorted(k for k, v in SIGNATURES.items() if v[1] != "split"))
         kinds = SIGNATURES[m][0]
         n = rng.randrange(0, 7)
         s = rand_str(rng, n, "ab" if m in ("replace", "replacen", "contains", "find", "rfind") else "abAB z\t")
@@ -180,6 +211,29 @@ def test_random_cases_match_oracle(Graph, fast):
             assert decode_result(m, got) == decode_result(m, ref), (m, args, padding)
         n_checked += 1
     assert n_checked > 80
+
+
+def test_split_family_random_cases(Graph):
+    """split family on random small inputs: empty pattern, pattern absent, overlapping matches ("aaaa" / "aa"),
+    n = 0, 1, larger than the number of pieces, leading / trailing / repeated separators"""
+    rng = random.Random(77)
+    methods = sorted(k for k, v in SIGNATURES.items() if v[1] == "split")
+    checked = 0
+    for _ in range(60):
+        m = rng.choice(methods)
+        s = "".join(rng.choice("ab. ") for _ in range(rng.randrange(0, 6)))
+        args = [s]
+        if m != "split_ascii_whitespace":
+            args.append(rng.choice(["", ".", "a", "aa", "ab", " ", "b."]))
+        if m in ("splitn", "rsplitn"):
+            args.append(rng.randrange(0, 5))
+        enc = encode_args(m, args, rng.randrange(0, 2))
+        ref = oracle_raw(m, enc)
+        got, _ = run_method(Graph, m, enc, 1)
+        assert [list(b) for b in got[0]] == [list(b) for b in ref[0]], (m, args)
+        assert int(got[1]) == int(ref[1]), (m, args)
+        checked += 1
+    assert checked == 60
 
 
 def test_fast_recording_is_shallow(Graph):
