@@ -40,6 +40,7 @@ constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-fr
 constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B: one padded 32 x 32 matrix
 constexpr int kWarpXbufDoubles = kXbufDoubles;  // per warp: ONE matrix (shared-memory carve-out 164 KB instead of 228 KB: 92 KB of L1 for twiddles and the BSK tile)
 constexpr int kPbsBaseLog = 23;
+constexpr int kBskPrefetch = 8;    // key rows per half-step requested ahead of the pair barrier (64 registers)
 
 struct alignas(16) cplx { double x, y; };
 
@@ -176,12 +177,20 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     for (int half = 0; half < 2; half++) {   // 16 spectrum rows at a time: the buffer holds 528 complex points
 #pragma unroll
         for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{re[half * 16 + q], im[half * 16 + q]};
+        // the first key words of this half do not depend on the partner: request them BEFORE the barrier so that
+        // their L2 latency overlaps the wait
+        cplx gsv[kBskPrefetch], gov[kBskPrefetch];
+#pragma unroll
+        for (int q = 0; q < kBskPrefetch; q++) {
+            gsv[q] = c.ldg(g + bsk_index(p, half * 16 + q, p, t));
+            gov[q] = c.ldg(g + bsk_index(1 - p, half * 16 + q, p, t));
+        }
         c.pair_sync();
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int k2 = half * 16 + q;
-            const cplx gs = c.ldg(g + bsk_index(p, k2, p, t));
-            const cplx go = c.ldg(g + bsk_index(1 - p, k2, p, t));
+            const cplx gs = q < kBskPrefetch ? gsv[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(p, k2, p, t));
+            const cplx go = q < kBskPrefetch ? gov[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(1 - p, k2, p, t));
             const cplx v = xp[q * 32 + t];
             const cplx s = cmul(cplx{re[k2], im[k2]}, gs);
             re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
