@@ -401,6 +401,45 @@ Char Graph::or_all(const std::vector<Char>& flags) {
     return flag_char(cur[0]);
 }
 
+// OR over windows of (AND over the window's flags), one level shallower than or_all(and_all(.)) when a window
+// reduces to two partial flags: two windows share one PBS on (a + b) + 4 (a' + b') -- both sums lie in {0,1,2},
+// the LUT fires when either is 2 (noise2 = 1 + 1 + 16 + 16 = 34, the reference's own worst case)
+Char Graph::or_of_ands(const std::vector<std::vector<BlockId>>& windows) {
+    std::vector<std::vector<BlockId>> w = windows;
+    bool all_two = !w.empty();
+    for (auto& flags : w) {
+        if (flags.empty()) return trivial_char(1);   // an empty AND is true
+        while (flags.size() > 2) {
+            std::vector<BlockId> nxt;
+            size_t i = 0;
+            for (size_t k : balanced_chunks(flags.size())) {
+                if (k == 1) { nxt.push_back(flags[i++]); continue; }
+                std::vector<std::pair<BlockId, int>> ops;
+                for (size_t j = 0; j < k; j++) ops.push_back({flags[i + j], 1});
+                nxt.push_back(pbs(ops, 0, table_of([k](int v) { return v == (int)k; })));
+                i += k;
+            }
+            flags.swap(nxt);
+        }
+        all_two = all_two && flags.size() == 2;
+    }
+    std::vector<Char> terms;
+    if (all_two) {
+        auto pair_tab = table_of([](int v) { return (int)(((v & 3) == 2) || ((v >> 2) == 2)); });
+        auto single_tab = table_of([](int v) { return (int)(v == 2); });
+        for (size_t i = 0; i + 1 < w.size(); i += 2)
+            terms.push_back(flag_char(pbs({{w[i][0], 1}, {w[i][1], 1}, {w[i + 1][0], 4}, {w[i + 1][1], 4}}, 0, pair_tab)));
+        if (w.size() % 2) terms.push_back(flag_char(pbs({{w.back()[0], 1}, {w.back()[1], 1}}, 0, single_tab)));
+    } else {
+        for (auto& flags : w) {
+            std::vector<Char> f;
+            for (auto b : flags) f.push_back(flag_char(b));
+            terms.push_back(and_all(f));
+        }
+    }
+    return or_all(terms);
+}
+
 // column compression: each column holds blocks of weight 4^c; chunks whose maximum sum is <= 15 are
 // replaced by (sum & 3) in the same column and (sum >> 2) in the next one.  Chunks are cut greedily from
 // the left, so sums over prefixes of one flag list share their leading chunks through CSE.
@@ -551,6 +590,14 @@ BlockId Graph::nibble_eq(BlockId a_lo, BlockId a_hi, BlockId b_lo, BlockId b_hi)
     if (a_lo == b_lo && a_hi == b_hi) return trivial_block(1);
     SignedScope sc(signed_ok);
     return pbs({{a_lo, 1}, {a_hi, 4}, {b_lo, -1}, {b_hi, -4}}, 0, table_of([](int v) { return v == 0; }));
+}
+
+std::vector<BlockId> Graph::nibble_eq_flags(const std::vector<std::pair<Char, Char>>& pairs) {
+    std::vector<BlockId> flags;
+    for (auto& pr : pairs)
+        for (int h = 0; h < 2; h++)
+            flags.push_back(nibble_eq(pr.first[2 * h], pr.first[2 * h + 1], pr.second[2 * h], pr.second[2 * h + 1]));
+    return flags;
 }
 
 Char Graph::block_and_eq(const std::vector<std::pair<Char, Char>>& pairs) {

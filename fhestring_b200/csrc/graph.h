@@ -104,6 +104,8 @@ public:
     Char nonzero(const Char& a);                      // a != 0 as one PBS over the block sum
     Char block_and_eq(const std::vector<std::pair<Char, Char>>& pairs);  // AND_i (a_i == b_i), nibble level
     BlockId nibble_eq(BlockId a_lo, BlockId a_hi, BlockId b_lo, BlockId b_hi);  // (a_lo + 4 a_hi) == (b_lo + 4 b_hi)
+    std::vector<BlockId> nibble_eq_flags(const std::vector<std::pair<Char, Char>>& pairs);  // two flags per char pair
+    Char or_of_ands(const std::vector<std::vector<BlockId>>& windows);  // OR_w AND_i flags[w][i], depth-minimised
     // generalisation of sum_flags: exact sum of 0/1 blocks as `ndigits` clean base-4 digits (little endian)
     std::vector<BlockId> sum_digits(const std::vector<BlockId>& flags, int ndigits);
     BlockId cond_bit(const Char& c);                  // c != 0 as a 0/1 block (scalar_ne(c, 0))

@@ -162,9 +162,13 @@ Char StringOps::contains(const Str& s, const Str& needle) {
     if (needle.size() > s.size()) return zero();
     const size_t end = s.size() - needle.size();
     if (fast) {
-        std::vector<Char> windows;
-        for (size_t i = 0; i <= end; i++) windows.push_back(match_at(s, i, needle, false));
-        return g.or_all(windows);
+        std::vector<std::vector<BlockId>> windows;
+        for (size_t i = 0; i <= end; i++) {
+            std::vector<std::pair<Char, Char>> pairs;
+            for (size_t j = 0; j < needle.size(); j++) pairs.push_back({needle[j], s[i + j]});
+            windows.push_back(g.nibble_eq_flags(pairs));
+        }
+        return g.or_of_ands(windows);
     }
     Char result = zero();
     for (size_t i = 0; i <= end; i++) {
