@@ -232,7 +232,7 @@ def contains_leg(eng, ck, stream, rank, world, steps, barrier):
         prog.close()
     g.close()
     out["workload"] = ("contains/find, encrypted 8-char pattern over a 256-char encrypted string (+1 NUL padding), "
-                       "depth-minimised graph, levels sharded over the ranks, NCCL all-gather per level")
+                       "depth-minimised graph, levels sharded over the ranks")
     out["reference_graph"] = {"contains_pbs_nominal": 19000, "contains_levels": 260, "source": "SURVEY.md 2.6"}
     return out
 
@@ -281,6 +281,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-contains", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU level exchange: P2P stores from the kernel epilogue + flag barrier (default) or NCCL all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args, out)
@@ -377,9 +379,18 @@ def main():
     # ---- string leg: contains()/find() latency, levels sharded over the ranks
     contains = None
     if not args.no_contains:
+        exchange = "none (1 GPU)"
         if world > 1:
-            eng.comm_init(rank, world)
+            if args.exchange == "p2p":
+                eng.peer_attach(rank, world)
+                exchange = "blind-rotation epilogue stores results into every peer arena over NVLink (cudaIpc) + flag barrier per level"
+            else:
+                eng.comm_init(rank, world)
+                exchange = "in-place ncclAllGather per level"
         contains = contains_leg(eng, ck, stream, rank, world, args.steps, barrier)
+        contains["exchange"] = exchange
+        if world > 1 and args.exchange == "p2p":
+            assert not eng.peer_timed_out(), "a peer barrier timed out"
 
     # ---- max over ranks
     t = torch.tensor([ms_total, e2e_ms, br_ms], device="cuda", dtype=torch.float64)

@@ -62,6 +62,34 @@ int launch_trivial(u64* arena, uint32_t first, uint32_t count, const uint8_t* va
     return 1;
 }
 
+// ---- cross-GPU level barrier over NVLink peer memory (one process per GPU, arenas and flag arrays mapped with
+// cudaIpc).  The blind rotation of a level has already stored its results into every peer's arena; this only
+// orders those stores before the next level anywhere reads them.
+struct PeerFlags { uint32_t* p[8]; };
+__global__ void peer_signal_kernel(PeerFlags peers, int rank, int world, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    __threadfence_system();   // the previous kernel's remote stores are complete at kernel end; keep the flag behind them
+    *reinterpret_cast<volatile uint32_t*>(peers.p[r] + rank) = epoch;
+}
+__global__ void peer_wait_kernel(uint32_t* my_flags, uint32_t* status, int rank, int world, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    const long long t0 = clock64();
+    while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(my_flags + r) - epoch) < 0) {
+        if (clock64() - t0 > 20000000000LL) { atomicExch(status, 1u); return; }   // ~10 s: a peer died; report, do not hang
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+int launch_peer_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, uint32_t* status, int rank, int world, uint32_t epoch, cudaStream_t s) {
+    PeerFlags pf{};
+    for (int r = 0; r < world && r < 8; r++) pf.p[r] = peer_flags[r];
+    peer_signal_kernel<<<1, 32, 0, s>>>(pf, rank, world, epoch);
+    peer_wait_kernel<<<1, 32, 0, s>>>(my_flags, status, rank, world, epoch);
+    return 2;
+}
+
 // ---- DFMA peak: 16 independent FMA chains per thread, 8 warps x 4 CTAs per SM
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {
     double a[16];

@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     job.init_acc = A.init_acc ? A.init_acc + (size_t)b * 2 * kN : nullptr;
     job.out_acc = A.out_acc ? A.out_acc + (size_t)b * 2 * kN : nullptr;
     job.out_lwe = A.jobs ? A.arena + (size_t)A.jobs[b].dst * (kN + 1) : nullptr;
+    if (A.jobs) {
+        job.n_peers = A.n_peers;
+        for (int r = 0; r < A.n_peers; r++) job.out_lwe_peer[r] = A.peer_arena[r] + (size_t)A.jobs[b].dst * (kN + 1);
+    }
     br_thread_main(c, job, A.bsk, A.tf, A.ti);
 }
 

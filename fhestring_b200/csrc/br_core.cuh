@@ -238,7 +238,13 @@ struct BrJobView {
     u64* out_lwe;         // optional [N+1]: sample-extracted LWE under the big key
     u64* out_acc;         // optional [2][N]: raw accumulator (test hook)
     int n;                // number of CMUX steps (small LWE dimension)
+    // multi-GPU: the same block of the PEER arenas (NVLink P2P stores); the sample-extract epilogue writes the
+    // result everywhere at once, so no collective follows the kernel
+    u64* out_lwe_peer[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_peers = 0;
 };
+
+constexpr int kMaxPeers = 7;
 
 template <class Ctx>
 FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const cplx* tf, const cplx* ti) {
@@ -277,10 +283,13 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
 #pragma unroll
             for (int m = 0; m < 64; m++) {
                 const int j = 32 * m + t;
-                job.out_lwe[j] = acc_to_u64((j == 0) ? acc[0] : (acc_t)0 - acc[kN - j]);
+                const u64 w = acc_to_u64((j == 0) ? acc[0] : (acc_t)0 - acc[kN - j]);
+                job.out_lwe[j] = w;
+                for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][j] = w;
             }
         } else if (t == 0) {
             job.out_lwe[kN] = acc_to_u64(acc[0]);
+            for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][kN] = acc_to_u64(acc[0]);
         }
     }
 }

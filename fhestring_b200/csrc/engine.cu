@@ -52,6 +52,13 @@ struct fhestr_engine {
     bool timing = false;
     struct Timed { cudaEvent_t a, b, c; uint32_t pbs; };   // a..b keyswitch, b..c blind rotation
     std::vector<Timed> timed;
+    // multi-GPU, preferred path: peer arenas mapped with cudaIpc; the blind-rotation epilogue stores every result
+    // into all arenas and a flag barrier over peer memory closes the level (no collective on the data path)
+    u64* peer_arena[8] = {};          // by rank; [rank] = own arena
+    uint32_t* peer_flags[8] = {};     // by rank; [rank] = own flag array
+    uint32_t* my_flags = nullptr;     // [8] epochs written by the peers + [8] = status word
+    bool peers_attached = false;
+    uint32_t epoch = 0;
     // multi-GPU (one process per GPU): NCCL communicator, resolved at run time from libnccl.so.2
     void* comm = nullptr;
     uint32_t rank = 0, world = 1;
@@ -227,6 +234,8 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->comm) fhestr_comm_destroy(e);
+    if (e->peers_attached) fhestr_peer_detach(e);
+    cudaFree(e->my_flags);
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
     cudaFree(e->bsk_q); cudaFree(e->qtab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
@@ -342,7 +351,7 @@ int fhestr_ct_trivial(fhestr_engine* e, uint32_t first, uint32_t count, const ui
 }
 
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
-static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all) {
+static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all, bool peer_stores = false) {
     if (n_pbs) {
         fhestr_engine::Timed t{};
         if (e->timing) {
@@ -358,7 +367,11 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
         br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
         br.bsk_q = e->bsk_q; br.qt = e->qt;
-        e->launches += e->pbs_per_cta == 8 ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+        br.n_peers = 0;
+        if (e->peers_attached && peer_stores) {
+            for (uint32_t r = 0; r < e->world; r++) if (r != e->rank) br.peer_arena[br.n_peers++] = e->peer_arena[r];
+        }
+        e->launches += (e->pbs_per_cta == 8 && !br.n_peers) ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
         if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
@@ -441,8 +454,8 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
     CK(cudaSetDevice(e->device));
     int rc = ensure_scratch(e, p->max_level_pbs);
     if (rc) return rc;
-    if (world > 1 && (!e->comm || e->world != world || e->rank != rank))
-        return fail(e, FHESTR_E_STATE, "multi-rank run needs fhestr_comm_init with the same rank/world");
+    if (world > 1 && ((!e->comm && !e->peers_attached) || e->world != world || e->rank != rank))
+        return fail(e, FHESTR_E_STATE, "multi-rank run needs fhestr_peer_attach or fhestr_comm_init with the same rank/world");
     for (uint32_t l = first_level; l < last_level; l++) {
         const uint32_t a = p->level_off[l], n_all = p->level_off[l + 1] - a, n_pbs = p->level_pbs[l];
         if (world == 1) {
@@ -459,8 +472,17 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
             const uint32_t first = p->level_first_dst[l];
             if (!p->level_contiguous[l] || (uint64_t)first + (uint64_t)per * world > e->arena_blocks)
                 return fail(e, FHESTR_E_INVALID, "level cannot be sharded: PBS results must be contiguous and padded to a multiple of world");
-            rc = run_level(e, p->d_jobs + a + lo, hi - lo, hi - lo);
+            rc = run_level(e, p->d_jobs + a + lo, hi - lo, hi - lo, e->peers_attached);
             if (rc) return rc;
+            if (e->peers_attached) {   // results are already in every arena: close the level with the flag barrier
+                e->launches += launch_peer_barrier(e->peer_flags, e->my_flags, e->my_flags + 8, (int)rank, (int)world, ++e->epoch, e->stream);
+                CK(cudaGetLastError());
+                if (n_all > n_pbs) {
+                    e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
+                    CK(cudaGetLastError());
+                }
+                continue;
+            }
             u64* base = e->arena + (size_t)first * (kN + 1);
             const size_t cnt = (size_t)per * (kN + 1);
             const int nr = nccl().AllGather(base + (size_t)rank * cnt, base, cnt, kNcclUint64, e->comm, e->stream);
@@ -470,6 +492,11 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
             e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
             CK(cudaGetLastError());
         }
+    }
+    if (world > 1 && e->peers_attached) {
+        // nobody starts rewriting this program's slots (next run) before every rank has finished reading them
+        e->launches += launch_peer_barrier(e->peer_flags, e->my_flags, e->my_flags + 8, (int)rank, (int)world, ++e->epoch, e->stream);
+        CK(cudaGetLastError());
     }
     return FHESTR_OK;
 }
@@ -488,6 +515,64 @@ void fhestr_shard_range(uint32_t n_jobs, uint32_t rank, uint32_t world, uint32_t
     if (lo) *lo = l;
     if (hi) *hi = h;
     if (per) *per = p;
+}
+
+int fhestr_peer_export(fhestr_engine* e, void* arena_handle_64, void* flags_handle_64) {
+    if (!e || !arena_handle_64 || !flags_handle_64) return FHESTR_E_INVALID;
+    if (!e->own_arena) return fail(e, FHESTR_E_STATE, "peer export needs an engine-owned arena");
+    CK(cudaSetDevice(e->device));
+    if (!e->my_flags) {
+        CK(cudaMalloc(&e->my_flags, 16 * sizeof(uint32_t)));
+        CK(cudaMemset(e->my_flags, 0, 16 * sizeof(uint32_t)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(arena_handle_64), e->arena));
+    CK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(flags_handle_64), e->my_flags));
+    return FHESTR_OK;
+}
+
+int fhestr_peer_attach(fhestr_engine* e, uint32_t rank, uint32_t world, const void* arena_handles, const void* flags_handles) {
+    if (!e || !arena_handles || !flags_handles || world < 2 || world > 8 || rank >= world) return FHESTR_E_INVALID;
+    if (!e->my_flags) return fail(e, FHESTR_E_STATE, "call fhestr_peer_export first");
+    if (e->peers_attached) return fail(e, FHESTR_E_STATE, "peers already attached");
+    CK(cudaSetDevice(e->device));
+    const cudaIpcMemHandle_t* ah = static_cast<const cudaIpcMemHandle_t*>(arena_handles);
+    const cudaIpcMemHandle_t* fh = static_cast<const cudaIpcMemHandle_t*>(flags_handles);
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank) { e->peer_arena[r] = e->arena; e->peer_flags[r] = e->my_flags; continue; }
+        void* pa = nullptr; void* pf = nullptr;
+        CK(cudaIpcOpenMemHandle(&pa, ah[r], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&pf, fh[r], cudaIpcMemLazyEnablePeerAccess));
+        e->peer_arena[r] = static_cast<u64*>(pa);
+        e->peer_flags[r] = static_cast<uint32_t*>(pf);
+    }
+    e->rank = rank; e->world = world; e->peers_attached = true; e->epoch = 0;
+    return FHESTR_OK;
+}
+
+int fhestr_peer_detach(fhestr_engine* e) {
+    if (!e) return FHESTR_E_INVALID;
+    if (e->peers_attached) {
+        cudaStreamSynchronize(e->stream);
+        for (uint32_t r = 0; r < e->world; r++) {
+            if (r == e->rank) continue;
+            if (e->peer_arena[r]) cudaIpcCloseMemHandle(e->peer_arena[r]);
+            if (e->peer_flags[r]) cudaIpcCloseMemHandle(e->peer_flags[r]);
+            e->peer_arena[r] = nullptr; e->peer_flags[r] = nullptr;
+        }
+        e->peers_attached = false;
+        if (!e->comm) { e->world = 1; e->rank = 0; }
+    }
+    return FHESTR_OK;
+}
+
+int fhestr_peer_status(fhestr_engine* e, uint32_t* timed_out) {
+    if (!e || !timed_out) return FHESTR_E_INVALID;
+    *timed_out = 0;
+    if (!e->my_flags) return FHESTR_OK;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(timed_out, e->my_flags + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return FHESTR_OK;
 }
 
 int fhestr_comm_unique_id(void* unique_id_128) {

@@ -20,6 +20,8 @@ struct BrBatchArgs {
     const cplx* ti;
     const u64* init_acc;      // optional [B][2][N]
     u64* out_acc;             // optional [B][2][N]
+    u64* peer_arena[7];       // arenas of the other ranks (cudaIpc-mapped), n_peers of them
+    int n_peers;
     const cplx* bsk_q;        // Fourier BSK, layout of the four-warp kernel (br_quad.cuh)
     QuadTables qt;
     int n;
@@ -55,6 +57,9 @@ cudaError_t keyswitch_mma_configure();
 int launch_ksk_limbs(const u64* ksk, int K, int n, unsigned char* out, cudaStream_t s);
 int ks_cols_padded(int n);
 size_t ks_digit_rows(size_t B);
+// cross-GPU level barrier over peer memory: every rank stores `epoch` into slot `rank` of each peer's flag array
+// (after a system-scope fence), then waits until its own array holds `epoch` in every slot.  Returns launches.
+int launch_peer_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, uint32_t* status, int rank, int world, uint32_t epoch, cudaStream_t s);
 // leveled jobs (lut < 0): dst = sum coeff*src + constant*e_body
 int launch_linear(const fhestr_job* jobs, int B, u64* arena, cudaStream_t s);
 // K5: 16-entry table -> body polynomial

@@ -179,6 +179,33 @@ class Engine:
         self._ck(self.lib.fhestr_comm_init(self.h, C.c_uint32(rank), C.c_uint32(world), uid.ctypes.data_as(C.c_void_p)))
         self.rank, self.world = rank, world
 
+    def peer_attach(self, rank: int, world: int):
+        """map every rank's arena with cudaIpc (handles carried by torch.distributed): results are stored into all
+        arenas by the blind-rotation epilogue, no collective on the data path"""
+        import torch
+        import torch.distributed as dist
+        mine = np.zeros(128, np.uint8)
+        self._ck(self.lib.fhestr_peer_export(self.h, mine[:64].ctypes.data_as(C.c_void_p), mine[64:].ctypes.data_as(C.c_void_p)))
+        t = torch.from_numpy(mine)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        allh = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        allh = np.stack([x.cpu().numpy() for x in allh])
+        ah, fh = np.ascontiguousarray(allh[:, :64]), np.ascontiguousarray(allh[:, 64:])
+        self._ck(self.lib.fhestr_peer_attach(self.h, C.c_uint32(rank), C.c_uint32(world), ah.ctypes.data_as(C.c_void_p),
+                                             fh.ctypes.data_as(C.c_void_p)))
+        self.rank, self.world = rank, world
+        dist.barrier()
+
+    def peer_detach(self):
+        self._ck(self.lib.fhestr_peer_detach(self.h))
+
+    def peer_timed_out(self) -> bool:
+        v = C.c_uint32()
+        self._ck(self.lib.fhestr_peer_status(self.h, C.byref(v)))
+        return bool(v.value)
+
     def comm_destroy(self):
         self._ck(self.lib.fhestr_comm_destroy(self.h))
 

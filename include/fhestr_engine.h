@@ -193,11 +193,21 @@ int fhestr_graph_execute(fhestr_graph* g, fhestr_engine* e, uint32_t rank, uint3
 int fhestr_graph_bind(fhestr_graph* g, fhestr_engine* e, fhestr_program** out);
 int fhestr_graph_commit(fhestr_graph* g);
 
-/* ---- multi-GPU: one process per GPU, keys replicated, one in-place NCCL all-gather per level ----------- */
+/* ---- multi-GPU: one process per GPU, keys and arena replicated; per level either P2P stores + flag barrier (peer_*)
+ * or one in-place NCCL all-gather (comm_*) ------------------------------------------------------------------ */
 /* unique_id: 128 bytes from fhestr_comm_unique_id on rank 0, handed to the other ranks by the host */
 int fhestr_comm_unique_id(void* unique_id_128);
 int fhestr_comm_init(fhestr_engine* e, uint32_t rank, uint32_t world, const void* unique_id_128);
 int fhestr_comm_destroy(fhestr_engine* e);
+/* Preferred multi-GPU data path: no collective at all.  Every rank exports its arena (and a small flag array)
+ * as cudaIpc handles (64 bytes each), the host exchanges them, fhestr_peer_attach maps the peers' memory; from
+ * then on the sample-extract epilogue of the blind rotation stores each result block into ALL arenas over NVLink
+ * and a flag barrier over peer memory closes the level.  arena_handles / flags_handles: [world][64] bytes by rank.
+ * fhestr_peer_status reports whether a barrier ever timed out (a peer died). */
+int fhestr_peer_export(fhestr_engine* e, void* arena_handle_64, void* flags_handle_64);
+int fhestr_peer_attach(fhestr_engine* e, uint32_t rank, uint32_t world, const void* arena_handles, const void* flags_handles);
+int fhestr_peer_detach(fhestr_engine* e);
+int fhestr_peer_status(fhestr_engine* e, uint32_t* timed_out);
 /* the slice of a level's n_jobs PBS jobs that `rank` of `world` computes: [lo, hi), per = ceil(n_jobs/world)
  * (the all-gather moves `per` blocks per rank, so a level's result slots are padded to per*world) */
 void fhestr_shard_range(uint32_t n_jobs, uint32_t rank, uint32_t world, uint32_t* lo, uint32_t* hi, uint32_t* per);
