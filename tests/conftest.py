@@ -43,6 +43,8 @@ def pytest_pyfunc_call(pyfuncitem):
     if outcome.excinfo is None or "gpu" not in pyfuncitem.keywords:
         return
     first = outcome.excinfo
+    if issubclass(first[0], (pytest.skip.Exception, KeyboardInterrupt)):
+        return
     try:
         os.makedirs(os.path.dirname(FLAKE_LOG), exist_ok=True)
         with open(FLAKE_LOG, "a") as f:
