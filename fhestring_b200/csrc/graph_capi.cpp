@@ -39,6 +39,7 @@ static uint32_t push_char(fhestr_graph* g, const Char& c) {
 
 #pragma GCC visibility push(default)
 extern "C" {
+int fhestr_graph_bind(fhestr_graph* g, fhestr_engine* e, fhestr_program** out);
 
 int fhestr_graph_create(int32_t delta_log, fhestr_graph** out) {
     if (!out || delta_log != 59) return FHESTR_E_INVALID;  // the recipes are written for 2 message + 2 carry bits
@@ -69,7 +70,7 @@ int fhestr_graph_trivial_chars(fhestr_graph* g, const uint8_t* values, uint32_t 
     return FHESTR_OK;
 }
 
-int fhestr_graph_char_op(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t* out) {
+static int graph_char_op_impl(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t* out) {
     if (!g || !out) return FHESTR_E_INVALID;
     const bool unary = op >= FHESTR_OP_IS_WHITESPACE;
     const bool ternary = op == FHESTR_OP_IF_THEN_ELSE;
@@ -101,7 +102,7 @@ int fhestr_graph_char_op(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32
     return FHESTR_OK;
 }
 
-int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+static int graph_string_op_impl(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
                            uint64_t clear_n, uint32_t* out_chars, uint32_t out_cap, uint32_t* out_len,
                            uint32_t* out_char) {
     if (!g || (!args && n_args)) return FHESTR_E_INVALID;
@@ -165,7 +166,7 @@ int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_s
     return FHESTR_OK;
 }
 
-int fhestr_graph_split_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+static int graph_split_op_impl(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
                           uint32_t* out_chars, uint32_t out_cap, uint32_t* n_buffers, uint32_t* buffer_len,
                           uint32_t* out_found) {
     if (!g || (!args && n_args) || !out_chars || !n_buffers || !buffer_len || !out_found) return FHESTR_E_INVALID;
@@ -210,7 +211,7 @@ int fhestr_graph_mark_output(fhestr_graph* g, const uint32_t* ids, uint32_t coun
     return FHESTR_OK;
 }
 
-int fhestr_graph_compile(fhestr_graph* g, uint32_t slot_align, fhestr_graph_info* info) {
+static int graph_compile_impl(fhestr_graph* g, uint32_t slot_align, fhestr_graph_info* info) {
     if (!g) return FHESTR_E_INVALID;
     std::string err;
     if (!g->g.compile(g->prog, err, slot_align)) return gfail(g, FHESTR_E_INVALID, err);
@@ -267,7 +268,7 @@ int fhestr_graph_char_slots(const fhestr_graph* g, const uint32_t* ids, uint32_t
     return FHESTR_OK;
 }
 
-int fhestr_graph_bind(fhestr_graph* g, fhestr_engine* e, fhestr_program** out) {
+static int graph_bind_impl(fhestr_graph* g, fhestr_engine* e, fhestr_program** out) {
     if (!g || !e || !out) return FHESTR_E_INVALID;
     if (!g->compiled) return gfail(g, FHESTR_E_STATE, "graph not compiled");
     if (g->bound != e) { g->bound = e; g->engine_lut.clear(); }
@@ -307,6 +308,70 @@ int fhestr_graph_execute(fhestr_graph* g, fhestr_engine* e, uint32_t rank, uint3
     fhestr_program_destroy(p);
     if (rc) return rc;
     return fhestr_graph_commit(g);
+}
+
+int fhestr_graph_char_op(fhestr_graph* g, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t* out) {
+    try {
+        return graph_char_op_impl(g, op, a, b, c, out);
+    } catch (const std::exception& ex) {   // nothing may unwind across the C ABI
+        if (g) g->err = std::string("fhestr_graph_char_op: ") + ex.what();
+        return FHESTR_E_STATE;
+    } catch (...) {
+        if (g) g->err = "fhestr_graph_char_op: unknown exception";
+        return FHESTR_E_STATE;
+    }
+}
+
+int fhestr_graph_string_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+                           uint64_t clear_n, uint32_t* out_chars, uint32_t out_cap, uint32_t* out_len,
+                           uint32_t* out_char) {
+    try {
+        return graph_string_op_impl(g, method, fast, args, n_args, clear_n, out_chars, out_cap, out_len, out_char);
+    } catch (const std::exception& ex) {   // nothing may unwind across the C ABI
+        if (g) g->err = std::string("fhestr_graph_string_op: ") + ex.what();
+        return FHESTR_E_STATE;
+    } catch (...) {
+        if (g) g->err = "fhestr_graph_string_op: unknown exception";
+        return FHESTR_E_STATE;
+    }
+}
+
+int fhestr_graph_split_op(fhestr_graph* g, int method, int fast, const fhestr_str_arg* args, uint32_t n_args,
+                          uint32_t* out_chars, uint32_t out_cap, uint32_t* n_buffers, uint32_t* buffer_len,
+                          uint32_t* out_found) {
+    try {
+        return graph_split_op_impl(g, method, fast, args, n_args, out_chars, out_cap, n_buffers, buffer_len, out_found);
+    } catch (const std::exception& ex) {   // nothing may unwind across the C ABI
+        if (g) g->err = std::string("fhestr_graph_split_op: ") + ex.what();
+        return FHESTR_E_STATE;
+    } catch (...) {
+        if (g) g->err = "fhestr_graph_split_op: unknown exception";
+        return FHESTR_E_STATE;
+    }
+}
+
+int fhestr_graph_compile(fhestr_graph* g, uint32_t slot_align, fhestr_graph_info* info) {
+    try {
+        return graph_compile_impl(g, slot_align, info);
+    } catch (const std::exception& ex) {   // nothing may unwind across the C ABI
+        if (g) g->err = std::string("fhestr_graph_compile: ") + ex.what();
+        return FHESTR_E_STATE;
+    } catch (...) {
+        if (g) g->err = "fhestr_graph_compile: unknown exception";
+        return FHESTR_E_STATE;
+    }
+}
+
+int fhestr_graph_bind(fhestr_graph* g, fhestr_engine* e, fhestr_program** out) {
+    try {
+        return graph_bind_impl(g, e, out);
+    } catch (const std::exception& ex) {   // nothing may unwind across the C ABI
+        if (g) g->err = std::string("fhestr_graph_bind: ") + ex.what();
+        return FHESTR_E_STATE;
+    } catch (...) {
+        if (g) g->err = "fhestr_graph_bind: unknown exception";
+        return FHESTR_E_STATE;
+    }
 }
 
 }  // extern "C"

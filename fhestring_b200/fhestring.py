@@ -263,9 +263,13 @@ class MyServerKey:
                 out.reshape(-1, self.engine.big)[i] = self.engine.download(int(s), 1)[0]
         return out
 
+    def _ids(self, a):
+        """char ids of one argument: an FheString, a list of FheAsciiChar (unpadded pattern) or a single char"""
+        chars = a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else list(a))
+        return self._adopt_all(chars) if chars else np.zeros(0, np.uint32)
+
     def _str(self, method, *args, clear_n=0):
-        ids = [self._adopt_all(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a))
-               for a in args]
+        ids = [self._ids(a) for a in args]
         rs, rc = self.graph.string_op(method, ids, fast=self.fast, clear_n=clear_n)
         s = None if rs is None else FheString([self._wrap(i) for i in rs])
         c = None if rc is None else self._wrap(rc)
@@ -315,9 +319,7 @@ class MyServerKey:
 
     # ---- split family (server_key/split.rs)
     def _split(self, method, *args):
-        ids = [self._adopt_all(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a))
-               if len(a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else a)) else np.zeros(0, np.uint32)
-               for a in args]
+        ids = [self._ids(a) for a in args]
         bufs, found = self.graph.split_op(method, ids, fast=self.fast)
         return FheSplit([FheString([self._wrap(i) for i in row]) for row in bufs], self._wrap(found))
 
