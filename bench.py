@@ -113,7 +113,9 @@ def cpu_port_rate(seconds_target: float = 12.0):
     dt, th = run(threads)                      # calibration (also warms caches)
     count = int(max(threads, min(BATCH, threads * max(1, round(seconds_target / max(dt, 1e-3))))))
     dt, th = run(count)
-    return count / dt, th, f"{count} of the {BATCH} blocks, {dt:.1f} s, oracle f64-FFT PBS (OpenMP over ciphertexts)"
+    return count / dt, th, (f"{count} of the {BATCH} blocks, {dt:.1f} s, oracle f64-FFT PBS (OpenMP over ciphertexts); a plain "
+                            "radix-2 C port of the tfhe-rs route -- tfhe-rs' own concrete-fft is several times faster per core "
+                            "(not measurable here: no Rust toolchain), so treat GPU/CPU ratios as upper bounds")
 
 
 def contains_leg(eng, ck, stream, rank, world, steps, barrier):
