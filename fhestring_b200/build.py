@@ -13,7 +13,7 @@ SOURCES = ["engine.cu", "blind_rotate.cu", "blind_rotate_quad.cu", "keyswitch.cu
 HEADERS = ["kernels.cuh", "br_core.cuh", "br_quad.cuh", "fft32_gen.cuh", "fft16_gen.cuh", "graph.h", "strings.h", os.path.join("..", "..", "include", "fhestr_engine.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wno-stringop-overflow",
 ]
 
 
@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
-        subprocess.check_call(["nvcc", "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-ldl"])
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+                               "-Xcompiler", "-fPIC", "-ldl"])
     return LIB
 
 
