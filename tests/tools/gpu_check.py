@@ -1,6 +1,8 @@
-"""Ad-hoc GPU bring-up check (not a test): parity of each kernel vs the oracle + first timings."""
+"""Ad-hoc GPU bring-up check (test infrastructure, lives under tests/ because it uses the oracle as the checker):
+parity of each kernel vs the oracle + timings of the blind-rotation launch shapes.
+usage: python tests/tools/gpu_check.py [batch] [--skip-small]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from fhestring_b200.engine import Engine, make_jobs, single_term_jobs, PARAM_MESSAGE_2_CARRY_2_KS_PBS as PE
