@@ -281,3 +281,42 @@ def test_compaction_network_exhaustive(Graph):
         s = [rng.choice([0, 0, rng.randrange(1, 128)]) for _ in range(L)]
         got, info = run_method(Graph, "concatenate", [s[:L // 2], s[L // 2:]], 1)
         assert list(got) == P.bubble_zeroes_right(s)
+
+
+def test_random_expression_dags_of_char_primitives(Graph):
+    """chains of the 11 FheAsciiChar primitives (results feeding later ops, flags mixed with u8 values, trivial
+    constants in between): the value-set / noise bookkeeping of the graph must hold for compositions, not only for
+    single ops"""
+    ops2 = {"eq": P.c_eq, "ne": P.c_ne, "le": P.c_le, "lt": P.c_lt, "ge": P.c_ge, "gt": P.c_gt, "bitand": P.c_and,
+            "bitor": P.c_or, "sub": P.c_sub, "add": P.c_add}
+    ops1 = {"is_whitespace": P.c_is_whitespace, "is_uppercase": P.c_is_uppercase, "is_lowercase": P.c_is_lowercase, "flip": P.c_flip}
+    rng = random.Random(2024)
+    for trial in range(12):
+        g = Graph()
+        n_in = 6
+        ids, slots = g.input_chars(n_in)
+        vals = [rng.choice([0, 1, 2, 9, 32, 65, 90, 97, 122, 127, 128, 200, 255, rng.randrange(256)]) for _ in range(n_in)]
+        pool = [(int(i), v) for i, v in zip(ids, vals)]
+        for c in (0, 1, 32, 255):
+            pool.append((int(g.trivial_chars([c])[0]), c))
+        outs = []
+        for step in range(40):
+            kind = rng.random()
+            if kind < 0.7:
+                name = rng.choice(sorted(ops2))
+                (a, va), (b, vb) = rng.choice(pool), rng.choice(pool)
+                node, val = g.char_op(name, a, b), ops2[name](va, vb)
+            elif kind < 0.85:
+                name = rng.choice(sorted(ops1))
+                a, va = rng.choice(pool)
+                node, val = g.char_op(name, a), ops1[name](va)
+            else:
+                (c, vc), (t, vt), (f, vf) = rng.choice(pool), rng.choice(pool), rng.choice(pool)
+                node, val = g.char_op("if_then_else", c, t, f), P.c_ite(vc, vt, vf)
+            pool.append((node, val))
+            outs.append((node, val))
+        g.mark_output([n for n, _ in outs])
+        g.compile()
+        values = run_program(g, slots.reshape(-1), blocks_of(vals).reshape(-1))
+        got = chars_of(values, g.char_slots([n for n, _ in outs]))
+        assert [int(v) for v in got] == [v for _, v in outs], trial
