@@ -202,3 +202,34 @@ def test_noise_of_deep_graph_outputs(keys):
     vals, err = ck.client.decrypt_blocks(cts.reshape(-1, ck.client.big), with_error=True)
     assert ck.decrypt(up) == "HELLO WORLD"
     assert np.abs(err).max() < (1 << 55)
+
+
+def test_every_arena_block_matches_the_plaintext_interpretation(keys):
+    """not only the decrypted outputs: EVERY block the compiled program writes (all intermediate PBS results and
+    leveled sums, padding-bit values included mod 16) equals the plaintext interpretation of the same job list"""
+    from fhestring_b200.graph import Graph
+    from plain_exec import blocks_of, run_program
+    ck, sk, pp = keys
+    sk.reset()
+    eng = sk.engine
+    for method, args in (("find", ["the quick brown fox", "brown"]), ("replace", ["hello world world", "world", "abc"]),
+                         ("ge", ["straw", "strap"]), ("trim", [" \tpadded \n"])):
+        enc = encode_args(method, args, 1)
+        g = Graph()
+        ids, slots, vals = [], [], []
+        for a in enc:
+            i, s = g.input_chars(len(a))
+            ids.append(i); slots.append(s.reshape(-1)); vals.append(blocks_of(a).reshape(-1))
+        rs, rc = g.string_op(method, ids, fast=True)
+        outs = ([] if rs is None else list(rs)) + ([] if rc is None else [rc])
+        g.mark_output(outs)
+        info = g.compile(1)
+        in_slots, in_vals = np.concatenate(slots), np.concatenate(vals)
+        eng.upload(int(in_slots[0]), ck.client.encrypt_blocks(in_vals.astype(np.uint8)))
+        plain = run_program(g, in_slots, in_vals)
+        jobs, off, npbs, first = g.program()
+        g.execute(eng)
+        got = ck.client.decrypt_blocks(eng.download(0, info.slots_used)).astype(np.int64)
+        written = np.array([int(j["dst"]) for j in jobs], np.int64)
+        assert np.array_equal(got[written], plain[written] % 16), method
+        g.close()
