@@ -138,7 +138,8 @@ static int ensure_scratch(fhestr_engine* e, size_t n_jobs) {
         e->ks_cap = n_jobs * 2 + 64;
         CK(cudaMalloc(&e->ks_out, e->ks_cap * (size_t)(e->prm.n + 1) * sizeof(u64)));
         CK(cudaMalloc(&e->ks_digits, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level));
-        CK(cudaMemset(e->ks_digits, 0, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level));
+        // on the engine stream: the stream is non-blocking, so a legacy-stream memset is NOT ordered before its kernels
+        CK(cudaMemsetAsync(e->ks_digits, 0, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level, e->stream));
         CK(cudaMalloc(&e->ks_body, e->ks_cap * sizeof(u64)));
     }
     return FHESTR_OK;
@@ -202,14 +203,16 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
     {
         std::vector<cplx> tf(1024), ti(1024);
         make_twiddles(tf.data(), ti.data());
-        CKC(cudaMemcpy(e->tf, tf.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpyAsync(e->tf, tf.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
+        CKC(cudaMemcpyAsync(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
+        CKC(cudaStreamSynchronize(e->stream));
     }
     CKC(cudaMalloc(&e->qtab, (1024 + 1024 + 64) * sizeof(cplx)));
     {
         std::vector<cplx> t(1024 + 1024 + 64);
         make_quad_tables(t.data(), t.data() + 1024, t.data() + 2048);
-        CKC(cudaMemcpy(e->qtab, t.data(), t.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpyAsync(e->qtab, t.data(), t.size() * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
+        CKC(cudaStreamSynchronize(e->stream));
         e->qt = QuadTables{e->qtab, e->qtab + 1024, e->qtab + 2048};
     }
     CKC(cudaMalloc(&e->bsk_q, (size_t)p->n * kQBskStepElems * sizeof(cplx)));
@@ -429,8 +432,12 @@ int fhestr_program_create(fhestr_engine* e, const fhestr_job* jobs, const uint32
         p->level_contiguous.push_back(contiguous);
     }
     cudaError_t ce = cudaMalloc(&p->d_jobs, (size_t)(total ? total : 1) * sizeof(fhestr_job));
+    // The upload goes on the ENGINE stream and is waited for.  A legacy-stream cudaMemcpy from pageable memory
+    // returns once the data are staged (the DMA may still be in flight), and the engine stream is non-blocking, so the
+    // first level's kernels could read whatever a recycled allocation still held: a stale job list.
     if (ce == cudaSuccess)
-        ce = cudaMemcpy(p->d_jobs, sorted.data(), (size_t)total * sizeof(fhestr_job), cudaMemcpyHostToDevice);
+        ce = cudaMemcpyAsync(p->d_jobs, sorted.data(), (size_t)total * sizeof(fhestr_job), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) {
         cudaFree(p->d_jobs);
         delete p;
@@ -523,7 +530,8 @@ int fhestr_peer_export(fhestr_engine* e, void* arena_handle_64, void* flags_hand
     CK(cudaSetDevice(e->device));
     if (!e->my_flags) {
         CK(cudaMalloc(&e->my_flags, 16 * sizeof(uint32_t)));
-        CK(cudaMemset(e->my_flags, 0, 16 * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(e->my_flags, 0, 16 * sizeof(uint32_t), e->stream));
+        CK(cudaStreamSynchronize(e->stream));
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     CK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(arena_handle_64), e->arena));
@@ -570,8 +578,8 @@ int fhestr_peer_status(fhestr_engine* e, uint32_t* timed_out) {
     if (!e || !timed_out) return FHESTR_E_INVALID;
     *timed_out = 0;
     if (!e->my_flags) return FHESTR_OK;
+    CK(cudaMemcpyAsync(timed_out, e->my_flags + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(timed_out, e->my_flags + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return FHESTR_OK;
 }
 
