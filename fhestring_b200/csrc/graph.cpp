@@ -356,7 +356,14 @@ Char Graph::flip(const Char& a) { return sub(trivial_char(1), a); }
 static const int kChunk = 15;
 
 // chunk sizes of a balanced reduction tree with fan-in <= kChunk: n inputs in ceil(n / kChunk) nearly equal chunks
+// -- except when one input is left over after full chunks (n = 16, 31, ...): it passes through as a chunk of one, which
+// saves a PBS at the same depth (16 nibble flags of an 8-char window: one PBS of 15 + the 16th flag, not two of 8)
 static std::vector<size_t> balanced_chunks(size_t n) {
+    if (n > 1 && n % kChunk == 1) {
+        std::vector<size_t> sizes(n / kChunk, (size_t)kChunk);
+        sizes.push_back(1);
+        return sizes;
+    }
     const size_t c = (n + kChunk - 1) / kChunk;
     std::vector<size_t> sizes(c, n / c);
     for (size_t i = 0; i < n % c; i++) sizes[i]++;
