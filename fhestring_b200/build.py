@@ -24,8 +24,12 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(HERE, "build")
+def build(force: bool = False, verbose: bool = False, slim: bool = False) -> str:
+    """slim=True builds the experimental blind-rotation variant (-DFHESTR_BR_SLIM=1, br_core.cuh) as
+    libfhestr_engine_slim.so next to the default library; select it with FHESTR_ENGINE_LIB for A/B runs."""
+    objdir = os.path.join(HERE, "build_slim" if slim else "build")
+    lib = os.path.join(HERE, "libfhestr_engine_slim.so") if slim else LIB
+    flags = NVCC_FLAGS + (["-DFHESTR_BR_SLIM=1"] if slim else [])
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -34,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         path = os.path.join(CSRC, src)
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         if force or _stale(obj, [path] + hdrs):
-            cmd = ["nvcc", *NVCC_FLAGS, "-x", "cu", "-c", path, "-o", obj]
+            cmd = ["nvcc", *flags, "-x", "cu", "-c", path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             subprocess.check_call(cmd)
@@ -42,11 +46,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    if force or _stale(LIB, objs):
-        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+    if force or _stale(lib, objs):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs,
                                "-Xcompiler", "-fPIC", "-ldl"])
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, slim="--slim" in sys.argv))

@@ -29,6 +29,15 @@
 #endif
 #include "fft32_gen.cuh"
 
+// FHESTR_BR_SLIM=1 builds the experimental "slim prologue" variant (see cmux_step): the accumulator buffers sit on
+// 8 KiB-aligned shared addresses so the rotation gather forms each address with ONE logic op, and the signed digit
+// keeps -2^22 instead of mapping it to +2^22 (both are the same torus value; |digit| is the same).  The integer
+// prologue is instruction-fetch bound (profiles/r1_br_stall_breakdown.md), so fewer instructions there is fewer
+// fetched lines.  Default 0: the measured kernel.
+#ifndef FHESTR_BR_SLIM
+#define FHESTR_BR_SLIM 0
+#endif
+
 namespace fhestr {
 
 typedef unsigned long long u64;
@@ -75,6 +84,9 @@ FHE_HD double digit23(acc_t x) {
     if (d == -(1 << 22)) d = (1 << 22);
     return (double)d;
 }
+
+// slim variant: the tie x = 2^31 - 256 .. 2^31 - 1 stays -2^22 (same torus value as +2^22, two instructions fewer)
+FHE_HD double digit23_slim(acc_t x) { return (double)(((int32_t)(x + (1u << 8))) >> 9); }
 
 // coefficient j of X^e * P (negacyclic), e in [0, 2N); generic word type
 template <class T>
@@ -160,12 +172,23 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     acc_t* acc = c.acc();
     double re[32], im[32];
     // rotate, subtract, decompose
+#if FHESTR_BR_SLIM
+    // byte offset of coefficient (t - e) mod 2N in the 2N-word negacyclic extension; row n1 adds 128 bytes.  Bit 13
+    // of the running offset is the sign, bits 2..12 the word inside the 8 KiB buffer (c.acc_ld_rot)
+    const uint32_t x0 = (uint32_t)((t - e) & (2 * kN - 1)) << 2;
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        re[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1) - a[n1]);
+        im[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1 + 4096u) - a[32 + n1]);
+    }
+#else
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
         const int j = 32 * n1 + t;
         re[n1] = digit23(rot_coef(acc, j, e) - a[n1]);
         im[n1] = digit23(rot_coef(acc, j + kM, e) - a[32 + n1]);
     }
+#endif
     forward1024(c, re, im, tf);
     // Fourier-domain GGSW product.  The two warps swap their spectra through the transpose buffers (1024 complex
     // points fit in the two matrices) and each forms ITS output polynomial completely:

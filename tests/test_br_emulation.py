@@ -11,15 +11,18 @@ import pytest
 from conftest import ROOT, monomial_mul
 
 
-@pytest.fixture(scope="module")
-def emu():
+# both builds of the thread program: the default kernel and the experimental slim-prologue variant (FHESTR_BR_SLIM)
+@pytest.fixture(scope="module", params=[0, 1], ids=["default", "slim"])
+def emu(request):
+    slim = request.param
     src = os.path.join(ROOT, "tests", "emu", "br_emu.cpp")
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libbr_emu.so")
+    lib = os.path.join(out_dir, "libbr_emu_slim.so" if slim else "libbr_emu.so")
     deps = [src] + [os.path.join(ROOT, "fhestring_b200", "csrc", f) for f in ("br_core.cuh", "fft32_gen.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", lib, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DFHESTR_BR_SLIM={slim}",
+                               "-o", lib, src])
     return C.CDLL(lib)
 
 
