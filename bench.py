@@ -423,9 +423,9 @@ def main():
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (4096 PBS),
-                # from the ncu --set full capture in profiles/r1_final_blind_rotate_ncu_full.csv (100.5 MB + 69.2 MB);
+                # from the ncu --set full capture in profiles/r1_final2_blind_rotate_ncu_full.csv (95.1 MB + 70.3 MB);
                 # algorithmic bytes: 24.3 MB keyswitched inputs + 67.1 MB outputs + 48.6 MB Fourier BSK = 140.0 MB
-                "traffic": 169.7e6 if B == BATCH else None, "traffic_unit": "bytes per launch",
+                "traffic": 165.4e6 if B == BATCH else None, "traffic_unit": "bytes per launch",
                 "kernel": "blind_rotate_kernel", "ms_per_launch": br_avg_ms,
                 "flops_per_launch": (br_pbs / max(1, br_launches)) * FLOPS_PER_PBS,
                 "peak_source": "DFMA microbenchmark measured in this run (fhestr_measure_fp64_peak); "

@@ -24,12 +24,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, slim: bool = False) -> str:
-    """slim=True builds the experimental blind-rotation variant (-DFHESTR_BR_SLIM=1, br_core.cuh) as
-    libfhestr_engine_slim.so next to the default library; select it with FHESTR_ENGINE_LIB for A/B runs."""
-    objdir = os.path.join(HERE, "build_slim" if slim else "build")
-    lib = os.path.join(HERE, "libfhestr_engine_slim.so") if slim else LIB
-    flags = NVCC_FLAGS + (["-DFHESTR_BR_SLIM=1"] if slim else [])
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple[str, ...] = ()) -> str:
+    """variant="tag" with defines=("NAME=VALUE", ...) builds an experimental kernel variant (the FHESTR_BR_* switches
+    of br_core.cuh) as libfhestr_engine_<tag>.so next to the default library; select it with FHESTR_ENGINE_LIB for
+    A/B runs (scripts/r1_ab_gpu_call.sh)."""
+    objdir = os.path.join(HERE, f"build_{variant}" if variant else "build")
+    lib = os.path.join(HERE, f"libfhestr_engine_{variant}.so") if variant else LIB
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -53,4 +54,9 @@ def build(force: bool = False, verbose: bool = False, slim: bool = False) -> str
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, slim="--slim" in sys.argv))
+    # usage: build.py [--force] [-v] [--variant TAG NAME=VALUE ...]
+    tag, defs = "", ()
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        tag, defs = sys.argv[i + 1], tuple(a for a in sys.argv[i + 2:] if "=" in a)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=tag, defines=defs))

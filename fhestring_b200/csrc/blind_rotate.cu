@@ -3,9 +3,11 @@
 //
 // Mapping: one PBS = one pair of warps (mask polynomial, body polynomial), one PBS per 64-thread CTA, 4 CTAs
 // per SM (255 registers/thread fill the 64K-register file: 8 warps, 2 per SM sub-partition).
-// Shared memory per pair: accumulator 2 x 2048 words on the 32-bit torus (16 KiB) + one padded transpose
-// matrix per warp (2 x 8448 B) + the mod-switched mask (2 KiB) = 35 328 B: 4 CTAs fit the 164 KB carve-out, which
+// Shared memory per pair: the mod-switched mask (2 KiB), the accumulator 2 x 2048 words on the 32-bit torus (16 KiB,
+// each polynomial on an 8 KiB-aligned shared address: 5 KiB of padding behind the mask) and one padded transpose
+// matrix per warp (2 x 8448 B) = 40 448 B: 4 CTAs (+ 1 KiB reserved each) still fit the 164 KB carve-out, which
 // leaves 92 KB of L1 for the twiddle tables and the BSK tile the 4 CTAs of an SM read at nearly the same time.
+// (FHESTR_BR_SLIM=0 is the unaligned 35 328 B layout of the first round-1 kernel.)
 // The Fourier BSK (46 MiB for n = 742) stays resident in the 126 MB L2 and is read with 16-byte
 // read-only loads, one 64 KiB step tile per CMUX.
 #include "kernels.cuh"
@@ -16,7 +18,7 @@ constexpr int kAtildeBytes = 2048;  // up to 1024 u16
 constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
 [[maybe_unused]] constexpr int kPairSmemBytes = kAccBytes + 2 * kWarpXbufDoubles * 8 + kAtildeBytes;  // 35 328 B
 #if FHESTR_BR_SLIM
-// slim variant (one PBS per CTA only): [mask 2 KiB][pad][acc0 8 KiB | acc1 8 KiB, each on an 8 KiB-aligned SHARED
+// aligned layout (one PBS per CTA only): [mask 2 KiB][pad][acc0 8 KiB | acc1 8 KiB, each on an 8 KiB-aligned SHARED
 // address][two transpose matrices].  The CTA's shared window starts at 0x400 (1 KiB is reserved per CTA), so the
 // pad is 5 KiB: 40 448 B per CTA, and 4 x (40 448 + 1 024) = 162 KiB still fits the 164 KiB carve-out.  The kernel
 // computes the pad from the real address and traps if the dynamic allocation is too small for it.
@@ -124,7 +126,7 @@ cudaError_t blind_rotate_configure() {
 }
 #endif
 
-// pbs_per_cta: 0 = default (1).  Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255
+// pbs_per_cta: 0 = default (1); 2 and 4 exist only in FHESTR_BR_SLIM=0 builds (the default build runs 1).  Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255
 // registers is the fastest shape; independent CTAs drift out of phase and overlap their FP64 and shared-memory
 // phases, while 2 or 4 PBS per CTA run in lockstep (1.3-1.5x slower), and sizing the register allocation for
 // 5-6 CTAs per SM (168 registers) makes every warp ~1.6x slower for 1.5x the warps (net 0.8x).

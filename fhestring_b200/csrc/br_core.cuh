@@ -29,13 +29,17 @@
 #endif
 #include "fft32_gen.cuh"
 
-// FHESTR_BR_SLIM=1 builds the experimental "slim prologue" variant (see cmux_step): the accumulator buffers sit on
-// 8 KiB-aligned shared addresses so the rotation gather forms each address with ONE logic op, and the signed digit
-// keeps -2^22 instead of mapping it to +2^22 (both are the same torus value; |digit| is the same).  The integer
-// prologue is instruction-fetch bound (profiles/r1_br_stall_breakdown.md), so fewer instructions there is fewer
-// fetched lines.  Default 0: the measured kernel.
+// Compile-time switches of the step (A/B-measured on one B200, profiles/r1_final2_ab_variants.md; build.py --variant
+// builds any other setting as a second library for FHESTR_ENGINE_LIB):
+//   FHESTR_BR_SLIM=1 (default)  the accumulator buffers sit on 8 KiB-aligned shared addresses so the rotation gather
+//       forms each address with ONE logic op, and the signed digit keeps -2^22 instead of mapping it to +2^22 (the
+//       same torus value, |digit| unchanged).  The integer prologue is instruction-fetch bound
+//       (profiles/r1_br_stall_breakdown.md): 8 instead of 12 instructions per coefficient, loop 3 812 -> 3 554.
+//       0 = the first round-1 kernel (also the only form with 2 or 4 PBS per CTA).
+//   FHESTR_BR_CVT_FP64=4 (default)  every 4th torus conversion of the epilogue runs on the FP64 pipe, see below.
+//   FHESTR_BR_PREFETCH=8, FHESTR_BR_I2F_FP64=0: measured, no gain beyond noise.
 #ifndef FHESTR_BR_SLIM
-#define FHESTR_BR_SLIM 0
+#define FHESTR_BR_SLIM 1
 #endif
 
 namespace fhestr {
@@ -49,7 +53,15 @@ constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-fr
 constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B: one padded 32 x 32 matrix
 constexpr int kWarpXbufDoubles = kXbufDoubles;  // per warp: ONE matrix (shared-memory carve-out 164 KB instead of 228 KB: 92 KB of L1 for twiddles and the BSK tile)
 constexpr int kPbsBaseLog = 23;
-constexpr int kBskPrefetch = 8;    // key rows per half-step requested ahead of the pair barrier (64 registers)
+#ifndef FHESTR_BR_PREFETCH
+#define FHESTR_BR_PREFETCH 8
+#endif
+constexpr int kBskPrefetch = FHESTR_BR_PREFETCH;    // key rows per half-step requested ahead of the pair barrier (8 = 64 registers)
+// FHESTR_BR_CVT_FP64 = m > 0: every m-th torus conversion of the epilogue runs on the FP64 pipe (four FP64 instructions,
+// bit-identical to the F2I) instead of the conversion unit, which sustains one F2I.S64 per 8 cycles per sub-partition
+#ifndef FHESTR_BR_CVT_FP64
+#define FHESTR_BR_CVT_FP64 4
+#endif
 
 struct alignas(16) cplx { double x, y; };
 
@@ -86,7 +98,27 @@ FHE_HD double digit23(acc_t x) {
 }
 
 // slim variant: the tie x = 2^31 - 256 .. 2^31 - 1 stays -2^22 (same torus value as +2^22, two instructions fewer)
-FHE_HD double digit23_slim(acc_t x) { return (double)(((int32_t)(x + (1u << 8))) >> 9); }
+// FHESTR_BR_I2F_FP64=1: the int -> double conversion of the digit as one DADD on the FP64 pipe instead of an I2F.F64 on
+// the conversion unit: the biased digit (x + 2^8 + 2^31) >> 9 in [0, 2^23) is dropped into the low mantissa word of
+// 2^52 and 2^52 + 2^22 is subtracted.  Exact, same value.
+#ifndef FHESTR_BR_I2F_FP64
+#define FHESTR_BR_I2F_FP64 0
+#endif
+FHE_HD double digit23_slim(acc_t x) {
+#if FHESTR_BR_I2F_FP64
+    const uint32_t biased = (x + ((1u << 8) + (1u << 31))) >> 9;
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(0x43300000, (int)biased) - 4503599631564800.0;   // 2^52 + 2^22
+#else
+    const u64 bits = 0x4330000000000000ull | biased;
+    double d;
+    __builtin_memcpy(&d, &bits, 8);
+    return d - 4503599631564800.0;
+#endif
+#else
+    return (double)(((int32_t)(x + (1u << 8))) >> 9);
+#endif
+}
 
 // coefficient j of X^e * P (negacyclic), e in [0, 2N); generic word type
 template <class T>
@@ -105,6 +137,28 @@ FHE_HD acc_t torus32_from_double(double x) {
 #else
     return (acc_t)(u64)(i64)llrint(x);
 #endif
+}
+
+// The same value on the FP64 pipe: r = rint(x 2^-32) by the 1.5 * 2^52 trick, x - r 2^32 is exact and lies in
+// [-2^31, 2^31], and adding 1.5 * 2^52 once more leaves round-to-nearest-even(x) mod 2^32 in the low mantissa word.
+FHE_HD acc_t torus32_from_double_fp64(double x) {
+    const double M = 6755399441055744.0;   // 1.5 * 2^52
+    const double r = fma(x, 1.0 / 4294967296.0, M) - M;
+    const double u = fma(r, -4294967296.0, x) + M;
+#ifdef __CUDA_ARCH__
+    return (acc_t)__double2loint(u);
+#else
+    u64 bits;
+    __builtin_memcpy(&bits, &u, 8);
+    return (acc_t)bits;
+#endif
+}
+FHE_HD acc_t torus32_conv(double x, int idx) {
+#if FHESTR_BR_CVT_FP64 > 0
+    if (idx % FHESTR_BR_CVT_FP64 == 0) return torus32_from_double_fp64(x);
+#endif
+    (void)idx;
+    return torus32_from_double(x);
 }
 
 // 32x32 transpose of one double per (lane, register) through the warp's padded buffer, real parts then imaginary
@@ -226,8 +280,8 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
         const int j = 32 * n1 + t;
-        a[n1] = acc[j] + torus32_from_double(re[n1]);
-        a[32 + n1] = acc[j + kM] + torus32_from_double(im[n1]);
+        a[n1] = acc[j] + torus32_conv(re[n1], n1);
+        a[32 + n1] = acc[j + kM] + torus32_conv(im[n1], n1);
         acc[j] = a[n1];
         acc[j + kM] = a[32 + n1];
     }

@@ -223,8 +223,9 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
 int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_mhz_hint);
 /* number of kernels this engine has launched so far (bench.py's gpu_launches) */
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
-/* blind-rotation launch shape override for experiments: PBS per CTA (1, 2 or 4; 0 = automatic); 8 selects the
- * four-warps-per-PBS kernel (br_quad.cuh) */
+/* blind-rotation launch shape override for experiments: PBS per CTA (0 = automatic = 1); 8 selects the
+ * four-warps-per-PBS kernel (br_quad.cuh); 2 and 4 (measured 1.3-1.5x slower) exist only in a library built with
+ * -DFHESTR_BR_SLIM=0 and run as 1 otherwise */
 int fhestr_set_pbs_per_cta(fhestr_engine* e, int pbs_per_cta);
 /* keyswitch implementation: 0 = tensor cores (u8 limb-split IMMA GEMM, default), 1 = CUDA cores (u64 IMAD);
  * both are exact and produce identical words */

@@ -11,18 +11,25 @@ import pytest
 from conftest import ROOT, monomial_mul
 
 
-# both builds of the thread program: the default kernel and the experimental slim-prologue variant (FHESTR_BR_SLIM)
-@pytest.fixture(scope="module", params=[0, 1], ids=["default", "slim"])
+# every build of the thread program: the default kernel and the experimental FHESTR_BR_* variants (br_core.cuh)
+VARIANTS = {
+    "default": (),   # aligned accumulator + every 4th torus conversion on the FP64 pipe
+    "first_r1_kernel": ("FHESTR_BR_SLIM=0", "FHESTR_BR_CVT_FP64=0"),
+    "all_fp64_conversions": ("FHESTR_BR_CVT_FP64=1", "FHESTR_BR_I2F_FP64=1"),
+}
+
+
+@pytest.fixture(scope="module", params=list(VARIANTS), ids=list(VARIANTS))
 def emu(request):
-    slim = request.param
+    tag = request.param
     src = os.path.join(ROOT, "tests", "emu", "br_emu.cpp")
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libbr_emu_slim.so" if slim else "libbr_emu.so")
+    lib = os.path.join(out_dir, f"libbr_emu_{tag}.so")
     deps = [src] + [os.path.join(ROOT, "fhestring_b200", "csrc", f) for f in ("br_core.cuh", "fft32_gen.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DFHESTR_BR_SLIM={slim}",
-                               "-o", lib, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC",
+                               *[f"-D{d}" for d in VARIANTS[tag]], "-o", lib, src])
     return C.CDLL(lib)
 
 
