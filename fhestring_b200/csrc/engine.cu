@@ -125,22 +125,28 @@ static int fail(fhestr_engine* e, int code, const std::string& msg) {
     return code;
 }
 
+// Grow the per-batch scratch.  A failed allocation leaves the capacity at 0 and the pointers null, so the next call
+// allocates again instead of running on freed memory.
 static int ensure_scratch(fhestr_engine* e, size_t n_jobs) {
     if (n_jobs > e->jobs_cap) {
-        if (e->d_jobs) CK(cudaFree(e->d_jobs));
-        e->jobs_cap = n_jobs * 2 + 64;
-        CK(cudaMalloc(&e->d_jobs, e->jobs_cap * sizeof(fhestr_job)));
+        e->jobs_cap = 0;
+        if (e->d_jobs) { CK(cudaFree(e->d_jobs)); e->d_jobs = nullptr; }
+        const size_t cap = n_jobs * 2 + 64;
+        CK(cudaMalloc(&e->d_jobs, cap * sizeof(fhestr_job)));
+        e->jobs_cap = cap;
     }
     if (n_jobs > e->ks_cap) {
-        if (e->ks_out) CK(cudaFree(e->ks_out));
-        if (e->ks_digits) CK(cudaFree(e->ks_digits));
-        if (e->ks_body) CK(cudaFree(e->ks_body));
-        e->ks_cap = n_jobs * 2 + 64;
-        CK(cudaMalloc(&e->ks_out, e->ks_cap * (size_t)(e->prm.n + 1) * sizeof(u64)));
-        CK(cudaMalloc(&e->ks_digits, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level));
+        e->ks_cap = 0;
+        if (e->ks_out) { CK(cudaFree(e->ks_out)); e->ks_out = nullptr; }
+        if (e->ks_digits) { CK(cudaFree(e->ks_digits)); e->ks_digits = nullptr; }
+        if (e->ks_body) { CK(cudaFree(e->ks_body)); e->ks_body = nullptr; }
+        const size_t cap = n_jobs * 2 + 64;
+        CK(cudaMalloc(&e->ks_out, cap * (size_t)(e->prm.n + 1) * sizeof(u64)));
+        CK(cudaMalloc(&e->ks_digits, ks_digit_rows(cap) * (size_t)kN * e->prm.ks_level));
         // on the engine stream: the stream is non-blocking, so a legacy-stream memset is NOT ordered before its kernels
-        CK(cudaMemsetAsync(e->ks_digits, 0, ks_digit_rows(e->ks_cap) * (size_t)kN * e->prm.ks_level, e->stream));
-        CK(cudaMalloc(&e->ks_body, e->ks_cap * sizeof(u64)));
+        CK(cudaMemsetAsync(e->ks_digits, 0, ks_digit_rows(cap) * (size_t)kN * e->prm.ks_level, e->stream));
+        CK(cudaMalloc(&e->ks_body, cap * sizeof(u64)));
+        e->ks_cap = cap;
     }
     return FHESTR_OK;
 }

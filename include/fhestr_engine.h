@@ -86,6 +86,8 @@ int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id)
 int fhestr_lut_download(fhestr_engine* e, int32_t lut_id, uint64_t* out_poly /* [N] */);
 
 /* ---- ciphertext arena (replaces owning BaseRadixCiphertext values, fheasciichar.rs:7-10) ------- */
+/* upload is asynchronous on the engine stream: a pageable `host` buffer is staged before the call returns, a PINNED
+ * one must stay valid until the next synchronising call (fhestr_sync, fhestr_ct_download) */
 int fhestr_ct_upload(fhestr_engine* e, uint32_t first_block, uint32_t count, const uint64_t* host);
 int fhestr_ct_download(fhestr_engine* e, uint32_t first_block, uint32_t count, uint64_t* host);
 /* create_trivial_radix (fheasciichar.rs:23): block b gets mask 0, body values[b] << delta_log */
