@@ -177,7 +177,15 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
             const float contrib = (float)ops[i].second * ops[i].second * n.noise2;
             if (contrib > worst_c) { worst_c = contrib; worst = (int)i; }
         }
-        if (worst < 0) { fail("noise budget exceeded and nothing to refresh"); break; }
+        if (worst < 0) {
+            std::string m = "noise budget exceeded and nothing to refresh:";
+            for (auto& op : ops) {
+                const BlockNode& n = nodes[op.first];
+                m += " (" + std::to_string(op.second) + " x kind " + std::to_string((int)n.kind) + " noise2 " + std::to_string(n.noise2) + ")";
+            }
+            fail(m);
+            break;
+        }
         ops[worst].first = refresh(ops[worst].first);
         flatten(ops, cst, terms, c);
     }
@@ -370,9 +378,18 @@ static std::vector<size_t> balanced_chunks(size_t n) {
     return sizes;
 }
 
+// AND and OR are idempotent: an operand that occurs twice (identical windows over trivial chars share one node through
+// CSE) is kept once, so that a sum never carries a coefficient > 1 on one PBS output (its noise would count squared)
+static void dedupe(std::vector<BlockId>& v) {
+    std::vector<BlockId> out;
+    for (auto b : v) if (std::find(out.begin(), out.end(), b) == out.end()) out.push_back(b);
+    v.swap(out);
+}
+
 Char Graph::and_all(const std::vector<Char>& flags) {
     std::vector<BlockId> cur;
     for (auto& c : flags) cur.push_back(cond_bit(c));
+    dedupe(cur);
     if (cur.empty()) return trivial_char(1);
     while (cur.size() > 1) {
         std::vector<BlockId> nxt;
@@ -392,6 +409,7 @@ Char Graph::and_all(const std::vector<Char>& flags) {
 Char Graph::or_all(const std::vector<Char>& flags) {
     std::vector<BlockId> cur;
     for (auto& c : flags) cur.push_back(cond_bit(c));
+    dedupe(cur);
     if (cur.empty()) return trivial_char(0);
     while (cur.size() > 1) {
         std::vector<BlockId> nxt;
@@ -415,6 +433,7 @@ Char Graph::or_of_ands(const std::vector<std::vector<BlockId>>& windows) {
     std::vector<std::vector<BlockId>> w = windows;
     bool all_two = !w.empty();
     for (auto& flags : w) {
+        dedupe(flags);
         if (flags.empty()) return trivial_char(1);   // an empty AND is true
         while (flags.size() > 2) {
             std::vector<BlockId> nxt;
@@ -464,9 +483,19 @@ std::vector<BlockId> Graph::sum_digits(const std::vector<BlockId>& flags, int nd
             while (i < col[c].size()) {
                 std::vector<std::pair<BlockId, int>> ops;
                 int total = 0;
-                while (i < col[c].size() && total + vmax(col[c][i]) <= 15 && ops.size() < FHESTR_MAX_TERMS) {
+                // a block that occurs m times in a chunk counts m^2 in the noise: close the chunk before the bound
+                std::map<BlockId, int> mult;
+                auto noise_with = [&](BlockId b) {
+                    float s2 = 0;
+                    for (auto& kv : mult) { const int m = kv.second + (kv.first == b ? 1 : 0); s2 += (float)m * m * nodes[kv.first].noise2; }
+                    if (!mult.count(b)) s2 += nodes[b].noise2;
+                    return s2;
+                };
+                while (i < col[c].size() && total + vmax(col[c][i]) <= 15 && ops.size() < FHESTR_MAX_TERMS &&
+                       (ops.empty() || noise_with(col[c][i]) <= kNoise2Limit)) {
                     total += vmax(col[c][i]);
                     ops.push_back({col[c][i], 1});
+                    mult[col[c][i]]++;
                     i++;
                 }
                 if (ops.size() == 1) { nxt[c].push_back(ops[0].first); continue; }
@@ -625,8 +654,11 @@ std::vector<Char> Graph::first_one_hot(const std::vector<Char>& flags, Char* any
     auto first_in = [&](const std::vector<BlockId>& v) {
         std::vector<BlockId> out;
         for (size_t i = 0; i < v.size(); i++) {
+            std::vector<BlockId> earlier(v.begin(), v.begin() + i);
+            dedupe(earlier);   // "some earlier flag is set" does not count repeats
+            if (std::find(earlier.begin(), earlier.end(), v[i]) != earlier.end()) { out.push_back(trivial_block(0)); continue; }
             std::vector<std::pair<BlockId, int>> ops;
-            for (size_t k = 0; k < i; k++) ops.push_back({v[k], 1});
+            for (auto b : earlier) ops.push_back({b, 1});
             ops.push_back({v[i], -1});
             out.push_back(pbs(ops, 1, is_zero_tab));
         }

@@ -59,6 +59,22 @@ Char StringOps::is_not_blank(const Char& c) {
     return g.flag_char(g.pbs({{h, 4}, {l, 1}}, 0, tc));
 }
 
+// 1 iff c is ASCII whitespace (0x09-0x0D, 0x20; NUL is not): the same two nibble classifiers, another combiner
+Char StringOps::is_blank_not_nul(const Char& c) {
+    std::array<uint8_t, 16> th{}, tl{}, tc{};
+    for (int v = 0; v < 16; v++) {
+        th[v] = v == 0 ? 1 : (v == 2 ? 2 : 0);
+        tl[v] = v == 0 ? 1 : ((v >= 9 && v <= 13) ? 2 : 0);
+    }
+    for (int v = 0; v < 16; v++) {
+        const int h = v >> 2, l = v & 3;
+        tc[v] = ((h == 1 && l == 2) || (h == 2 && l == 1)) ? 1 : 0;
+    }
+    const BlockId h = g.pbs({{c[3], 4}, {c[2], 1}}, 0, th);
+    const BlockId l = g.pbs({{c[1], 4}, {c[0], 1}}, 0, tl);
+    return g.flag_char(g.pbs({{h, 4}, {l, 1}}, 0, tc));
+}
+
 // flag: c in [first, first + 25] for first = 0x41 ('A'..'Z') or 0x61 ('a'..'z')
 static Char letter_range_flag(Graph& g, const Char& c, int first) {
     const int row = first >> 4;
@@ -84,9 +100,14 @@ static std::vector<BlockId> suffix_or(Graph& g, const std::vector<BlockId>& f) {
     std::vector<BlockId> out(n);
     if (n == 0) return out;
     std::vector<BlockId> chunk_or;
+    // OR is idempotent: a flag that occurs twice (shared node) is summed once, so no coefficient exceeds 1
+    auto add_once = [](std::vector<std::pair<BlockId, int>>& ops, BlockId b) {
+        for (auto& o : ops) if (o.first == b) return;
+        ops.push_back({b, 1});
+    };
     for (size_t c0 = 0; c0 < n; c0 += m) {
         std::vector<std::pair<BlockId, int>> ops;
-        for (size_t k = c0; k < std::min(n, c0 + m); k++) ops.push_back({f[k], 1});
+        for (size_t k = c0; k < std::min(n, c0 + m); k++) add_once(ops, f[k]);
         chunk_or.push_back(ops.size() == 1 ? ops[0].first : g.pbs(ops, 0, nz));
     }
     std::vector<BlockId> later;  // later[c] = OR of chunks > c
@@ -98,8 +119,8 @@ static std::vector<BlockId> suffix_or(Graph& g, const std::vector<BlockId>& f) {
         const size_t hi = std::min(n, c0 + m);
         for (size_t i = c0; i < hi; i++) {
             std::vector<std::pair<BlockId, int>> ops;
-            for (size_t k = i; k < hi; k++) ops.push_back({f[k], 1});
-            if (c < later.size()) ops.push_back({later[c], 1});
+            for (size_t k = i; k < hi; k++) add_once(ops, f[k]);
+            if (c < later.size()) add_once(ops, later[c]);
             out[i] = ops.size() == 1 ? ops[0].first : g.pbs(ops, 0, nz);
         }
     }
@@ -608,10 +629,10 @@ Str StringOps::trim_start(const Str& s) {
 Str StringOps::trim(const Str& s) { return trim_start(trim_end(s)); }
 
 // ------------------------------------------------------------------------------------ split.rs
-// The split family is recorded in the reference's own op order in both modes (its structure is a serial scan
-// over the string with L x L copy buffers); `fast` only selects how the inner replace / bubble_zeroes_right /
-// starts_with calls are recorded.  The graph folds what cannot change the value (trivial buffer indices,
-// untouched buffers).
+// Faithful mode records the reference's own op order (a serial scan over the string with L x L copy buffers; the
+// graph folds what cannot change the value: trivial buffer indices, untouched buffers).  Fast mode records the
+// plaintext-identical parallel form of the scan (split_scan_fast below, the fast branch of split_ascii_whitespace) and
+// of the chains inside clear_pattern_from_result, on top of the fast replace / bubble_zeroes_right / starts_with.
 Char StringOps::rsplit_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore) {
     Char found = one();
     if (pattern.empty()) {
@@ -673,6 +694,23 @@ void StringOps::handle_n_case(const Char& found, const Char* n, Char& ccb, Char&
 void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& result, const Str& pattern, bool inclusive, bool terminator) {
     const size_t size = result.size();
     const Str to(pattern.size(), zero());
+    if (n && fast) {
+        // stop_replacing after buffer i = OR_{k <= i} (n == k + 1): a prefix OR instead of a chain of size bitors
+        std::vector<BlockId> hit;
+        for (size_t i = 0; i < size; i++)
+            hit.push_back(g.block_and_eq({{*n, g.trivial_char((uint8_t)(((i & 255) + 1) & 255))}})[0]);
+        std::reverse(hit.begin(), hit.end());
+        std::vector<BlockId> stop = suffix_or(g, hit);
+        std::reverse(stop.begin(), stop.end());
+        for (size_t i = 0; i < size; i++) {
+            const Str current = bubble_zeroes_right(result[i]);
+            const Str replacement = replace(current, pattern, to);
+            const BlockId go = g.not_flag(stop[i]);
+            for (size_t j = 0; j < size; j++)
+                result[i][j] = g.add_disjoint({g.mul_flag_char(stop[i], current[j]), g.mul_flag_char(go, replacement[j])});
+        }
+        return;
+    }
     if (n) {
         Char stop_replacing = zero();
         for (size_t i = 0; i < size; i++) {
@@ -688,6 +726,25 @@ void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& resul
     } else {
         for (size_t i = 0; i < size; i++) result[i] = bubble_zeroes_right(result[i]);
     }
+    if (terminator && fast) {
+        // the last run of all-zero buffers that start with the pattern is deleted: non_zero_found before buffer i is the
+        // OR over the LATER buffers, a suffix OR instead of a chain
+        std::vector<BlockId> nz(size), sw(size);
+        for (size_t i = 0; i < size; i++) {
+            std::vector<Char> any;
+            for (size_t j = 0; j < size; j++) any.push_back(g.nonzero(result[i][j]));
+            nz[i] = g.or_all(any)[0];
+            sw[i] = g.cond_bit(starts_with(result[i], pattern));
+        }
+        const std::vector<BlockId> later = suffix_or(g, nz);   // later[i] = OR_{k >= i} nz[k]
+        for (size_t i = 0; i < size; i++) {
+            std::vector<Char> all{g.flag_char(sw[i]), g.flag_char(g.not_flag(nz[i]))};
+            if (i + 1 < size) all.push_back(g.flag_char(g.not_flag(later[i + 1])));
+            const BlockId keep = g.not_flag(g.and_all(all)[0]);
+            for (size_t j = 0; j < size; j++) result[i][j] = g.mul_flag_char(keep, result[i][j]);
+        }
+        return;
+    }
     if (terminator) {
         Char non_zero_found = zero();
         for (size_t ii = 0; ii < size; ii++) {
@@ -702,9 +759,118 @@ void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& resul
     }
 }
 
+// Depth-minimised scan of _split / _rsplit (split.rs:883-988, :307-393), plaintext-identical to the serial one:
+//  * the raw window matches come from the ORIGINAL string and are independent;
+//  * the `ignore` bookkeeping of the reference only ever blocks a match because of an EARLIER match whose marked range
+//    [i', i' + P - 1] meets the window: for split (windows END at i) that is a match at i' in [i - 2P + 2, i - 1], for
+//    rsplit (windows START at i, scanned downwards) one at i' in [i + 1, i + P - 1].  At most one match fits such a
+//    range, so found_i = raw_i AND no match in the range is ONE PBS on 2 raw_i + (sum of the range): one level per
+//    position instead of four;
+//  * the copy buffer index before position t is the number of matches seen so far -- capped at n - 1 in the n forms,
+//    where the reference stops incrementing once it reaches n - 1 -- and cell (j, t) takes s[t] iff it equals j.
+SplitResult StringOps::split_scan_fast(const Str& s, const Str& pattern, const Char* n, bool reverse) {
+    const size_t size = s.size(), P = pattern.size();
+    const BlockId f0 = g.trivial_block(0), f1 = g.trivial_block(1);
+    std::vector<BlockId> found(size, f0);
+    auto is2 = [](int v) { return (int)(v == 2); };
+    std::array<uint8_t, 16> is2_tab{}, nz_tab{};
+    for (int v = 0; v < 16; v++) { is2_tab[v] = (uint8_t)is2(v); nz_tab[v] = (uint8_t)(v != 0); }
+    // found_i from raw_i and the earlier matches at `range` (most recent first)
+    auto gate = [&](BlockId raw, std::vector<BlockId> range) {
+        if (g.is_trivial(raw) && g.trivial_value(raw) == 0) return f0;
+        std::vector<std::pair<BlockId, int>> ops{{raw, 2}};
+        const size_t direct = 12;   // 2 raw + 12 + 1 <= 15: the value-set analysis does not know that at most one flag of the range is set
+        if (range.size() > direct + 1) {   // the far end of the range was known long ago: fold it into one flag
+            std::vector<std::pair<BlockId, int>> far;
+            std::vector<BlockId> far_flags;
+            for (size_t k = direct; k < range.size(); k++) {
+                far.push_back({range[k], 1});
+                if (far.size() == 15) { far_flags.push_back(g.pbs(far, 0, nz_tab)); far.clear(); }
+            }
+            if (!far.empty()) far_flags.push_back(far.size() == 1 ? far[0].first : g.pbs(far, 0, nz_tab));
+            range.resize(direct);
+            std::vector<Char> ff;
+            for (auto b : far_flags) ff.push_back(g.flag_char(b));
+            range.push_back(g.or_all(ff)[0]);
+        }
+        for (auto b : range) ops.push_back({b, 1});
+        return g.pbs(ops, 0, is2_tab);
+    };
+    if (!reverse) {
+        for (size_t i = 0; i < size; i++) {
+            if (P > size || i + 1 < P) continue;
+            const BlockId raw = P == 0 ? f1 : g.cond_bit(match_at(s, i + 1 - P, pattern, false));
+            std::vector<BlockId> range;
+            for (size_t d = 1; d + 2 <= 2 * P && d <= i; d++) range.push_back(found[i - d]);   // i' in [i - 2P + 2, i - 1]
+            found[i] = gate(raw, range);
+        }
+    } else {
+        std::vector<BlockId> nzs;
+        if (P == 0) for (auto& c : s) nzs.push_back(g.cond_bit(g.nonzero(c)));
+        for (size_t ii = 0; ii < size; ii++) {
+            const size_t i = size - 1 - ii;
+            if (P == 0) {   // a pad right after the last char, or any non-pad char: nz_i OR nz_(i-1)
+                found[i] = i >= 1 ? g.pbs({{nzs[i], 1}, {nzs[i - 1], 1}}, 0, nz_tab) : nzs[i];
+                continue;
+            }
+            if (P > size || i + P >= size) continue;
+            const BlockId raw = g.cond_bit(match_at(s, i, pattern, false));
+            std::vector<BlockId> range;
+            for (size_t d = 1; d + 1 <= P && i + d < size; d++) range.push_back(found[i + d]);       // i' in [i + 1, i + P - 1]
+            found[i] = gate(raw, range);
+        }
+    }
+    // copy buffer index before each position, in scan order
+    std::vector<Char> seen;   // 0/1 chars counted so far
+    if (!reverse && P == 0 && n) {
+        const Char skip_first = g.bitand_(g.gt(*n, one()), g.le(*n, len(s)));   // split.rs:917-927
+        seen.push_back(skip_first);
+    }
+    const BlockId allow = n ? g.cond_bit(g.nonzero(*n)) : f1;
+    const Char cap = n ? g.sub(*n, one()) : zero();
+    std::vector<Str> result(size, Str(size, zero()));
+    for (size_t tt = 0; tt < size; tt++) {
+        const size_t t = reverse ? size - 1 - tt : tt;
+        const Char src = n ? g.mul_flag_char(allow, s[t]) : s[t];
+        std::vector<std::pair<BlockId, int>> live;
+        for (auto& c : seen) if (!(g.is_trivial(c[0]) && g.trivial_value(c[0]) == 0)) live.push_back({c[0], 1});
+        bool repeats = false;
+        for (size_t a = 0; a < live.size() && !repeats; a++)
+            for (size_t b = a + 1; b < live.size(); b++) if (live[a].first == live[b].first) { repeats = true; break; }
+        if (!n && live.size() <= 15 && !repeats) {
+            // ccb == j is one PBS on the sum of the flags seen so far
+            for (size_t j = 0; j < size && j <= live.size(); j++) {
+                std::array<uint8_t, 16> tab{};
+                tab[j & 15] = 1;
+                const BlockId hit = live.empty() ? (j == 0 ? f1 : f0) : g.pbs(live, 0, tab);
+                result[j][t] = g.mul_flag_char(hit, src);
+            }
+        } else {
+            Char ccb = g.sum_flags(seen);
+            if (n) {
+                const BlockId capped = g.cond_bit(g.ge(ccb, cap));
+                ccb = g.add_disjoint({g.mul_flag_char(capped, cap), g.mul_flag_char(g.not_flag(capped), ccb)});
+            }
+            for (size_t j = 0; j < size; j++) {
+                const BlockId hit = g.cond_bit(g.block_and_eq({{g.trivial_char((uint8_t)(j & 255)), ccb}}));
+                result[j][t] = g.mul_flag_char(hit, src);
+            }
+        }
+        seen.push_back(g.flag_char(found[t]));
+    }
+    std::vector<Char> any;
+    for (auto b : found) any.push_back(g.flag_char(b));
+    return SplitResult{result, g.or_all(any)};
+}
+
 SplitResult StringOps::rsplit_impl(const Str& s_in, const Str& pattern, bool inclusive, bool terminator, const Char* n) {
     Str s = s_in;
     s.push_back(zero());
+    if (fast) {
+        SplitResult r = split_scan_fast(s, pattern, n, true);
+        clear_pattern_from_result(n, r.buffers, pattern, inclusive, terminator);
+        return r;
+    }
     const size_t size = s.size();
     Char ccb = zero(), stop = zero(), found_any = zero();
     std::vector<Str> result(size, Str(size, zero()));
@@ -724,6 +890,11 @@ SplitResult StringOps::rsplit_impl(const Str& s_in, const Str& pattern, bool inc
 SplitResult StringOps::split_impl(const Str& s_in, const Str& pattern, bool inclusive, bool terminator, const Char* n) {
     Str s = s_in;
     s.push_back(zero());
+    if (fast) {
+        SplitResult r = split_scan_fast(s, pattern, n, false);
+        clear_pattern_from_result(n, r.buffers, pattern, inclusive, terminator);
+        return r;
+    }
     const size_t size = s.size();
     Char ccb = zero(), stop = zero(), found_any = zero();
     std::vector<Str> result(size, Str(size, zero()));
@@ -745,6 +916,43 @@ SplitResult StringOps::split_impl(const Str& s_in, const Str& pattern, bool incl
 
 SplitResult StringOps::split_ascii_whitespace(const Str& s) {
     const size_t size = s.size();
+    if (fast) {
+        // the buffer index at position i is the number of (whitespace after non-whitespace) transitions up to and
+        // including i; only non-whitespace chars are ever copied, so the reference's second pass (whitespace -> NUL
+        // inside the buffers, split.rs:1425-1434) cannot change a value and is not recorded
+        std::vector<BlockId> ws(size), inc(size);
+        std::array<uint8_t, 16> is1{};
+        is1[1] = 1;
+        for (size_t i = 0; i < size; i++) ws[i] = is_blank_not_nul(s[i])[0];
+        for (size_t i = 0; i < size; i++)
+            inc[i] = i == 0 ? g.trivial_block(0) : g.pbs({{ws[i], 1}, {ws[i - 1], 2}}, 0, is1);
+        std::vector<Str> result(size, Str(size, zero()));
+        std::vector<Char> seen;
+        for (size_t i = 0; i < size; i++) {
+            seen.push_back(g.flag_char(inc[i]));
+            const Char src = g.mul_flag_char(g.not_flag(ws[i]), s[i]);
+            std::vector<std::pair<BlockId, int>> live;
+            for (auto& c : seen) if (!(g.is_trivial(c[0]) && g.trivial_value(c[0]) == 0)) live.push_back({c[0], 1});
+            if (live.size() <= 15) {
+                for (size_t j = 0; j < size && j <= live.size(); j++) {
+                    std::array<uint8_t, 16> tab{};
+                    tab[j & 15] = 1;
+                    const BlockId hit = live.empty() ? g.trivial_block(j == 0 ? 1 : 0) : g.pbs(live, 0, tab);
+                    result[j][i] = g.mul_flag_char(hit, src);
+                }
+            } else {
+                const Char ccb = g.sum_flags(seen);
+                for (size_t j = 0; j < size; j++) {
+                    const BlockId hit = g.cond_bit(g.block_and_eq({{g.trivial_char((uint8_t)(j & 255)), ccb}}));
+                    result[j][i] = g.mul_flag_char(hit, src);
+                }
+            }
+        }
+        for (size_t j = 0; j < size; j++) result[j] = bubble_zeroes_right(result[j]);
+        std::vector<Char> any;
+        for (auto b : ws) any.push_back(g.flag_char(b));
+        return SplitResult{result, g.or_all(any)};
+    }
     Char ccb = zero(), prev_ws = one(), found_any = zero();
     std::vector<Str> result(size, Str(size, zero()));
     for (size_t i = 0; i < size; i++) {

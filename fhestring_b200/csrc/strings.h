@@ -74,10 +74,12 @@ private:
     Str handle_shorter_from(const Str& bytes, const Str& from, const Str& to, const Char& n, bool use_counter);
     std::vector<Char> last_one_hot(const std::vector<Char>& flags, Char* any);
     Char is_not_blank(const Char& c);
+    Char is_blank_not_nul(const Char& c);
     Char rsplit_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);   // split.rs:10
     Char split_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);    // split.rs:70
     void copy_logic(size_t i, const Char* n, const Str& s, std::vector<Str>& result, const Char& allow, const Char& ccb);  // :108
     void handle_n_case(const Char& found, const Char* n, Char& ccb, Char& stop);              // split.rs:137
+    SplitResult split_scan_fast(const Str& s, const Str& pattern, const Char* n, bool reverse);   // parallel form of the scans of :307 / :883
     void clear_pattern_from_result(const Char* n, std::vector<Str>& result, const Str& pattern, bool inclusive, bool terminator);  // :180
 };
 

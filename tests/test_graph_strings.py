@@ -214,26 +214,49 @@ def test_random_cases_match_oracle(Graph, fast):
 
 
 def test_split_family_random_cases(Graph):
-    """split family on random small inputs: empty pattern, pattern absent, overlapping matches ("aaaa" / "aa"),
-    n = 0, 1, larger than the number of pieces, leading / trailing / repeated separators"""
+    """split family on random inputs, every buffer compared raw with the oracle: empty pattern, pattern absent,
+    overlapping matches ("aaaa" / "aa"), n = 0, 1, larger than the number of pieces, 255; leading / trailing / repeated
+    separators; strings with more than 15 matches (the counted form of the buffer index) and 8-9 char patterns (the
+    folded far end of the blocking range in the depth-minimised scan)"""
     rng = random.Random(77)
     methods = sorted(k for k, v in SIGNATURES.items() if v[1] == "split")
     checked = 0
-    for _ in range(60):
+    for _ in range(140):
         m = rng.choice(methods)
-        s = "".join(rng.choice("ab. ") for _ in range(rng.randrange(0, 6)))
+        mode = rng.random()
+        if mode < 0.6:
+            s = "".join(rng.choice("ab. ") for _ in range(rng.randrange(0, 6)))
+            pats = ["", ".", "a", "aa", "ab", " ", "b.", "aba"]
+        elif mode < 0.85:
+            s = "".join(rng.choice("ab") for _ in range(rng.randrange(8, 20)))
+            pats = ["a", "ab", "aab", "abab", "b", ""]
+        else:
+            p = "".join(rng.choice("ab") for _ in range(rng.randrange(8, 10)))
+            s = (p + "b") * 2 + "".join(rng.choice("ab") for _ in range(rng.randrange(0, 4)))
+            pats = [p]
         args = [s]
         if m != "split_ascii_whitespace":
-            args.append(rng.choice(["", ".", "a", "aa", "ab", " ", "b."]))
+            args.append(rng.choice(pats))
+        else:
+            args = ["".join(rng.choice("ab \t\n") for _ in range(rng.randrange(0, 20)))]
         if m in ("splitn", "rsplitn"):
-            args.append(rng.randrange(0, 5))
-        enc = encode_args(m, args, rng.randrange(0, 2))
+            args.append(rng.choice([0, 1, 2, 3, 4, 7, 17, 255]))
+        enc = encode_args(m, args, rng.randrange(0, 3))
         ref = oracle_raw(m, enc)
         got, _ = run_method(Graph, m, enc, 1)
         assert [list(b) for b in got[0]] == [list(b) for b in ref[0]], (m, args)
         assert int(got[1]) == int(ref[1]), (m, args)
         checked += 1
-    assert checked == 60
+    assert checked == 140
+
+
+def test_fast_split_scan_is_shallow(Graph):
+    """the depth-minimised scan: one level per position instead of four (the reference's op order: 29 levels)"""
+    enc = encode_args("split", ["hello", "ello"], 1)
+    got_fast, info_fast = run_method(Graph, "split", enc, 1)
+    got_ref, info_ref = run_method(Graph, "split", enc, 0)
+    assert [list(b) for b in got_fast[0]] == [list(b) for b in got_ref[0]] == [list(b) for b in oracle_raw("split", enc)[0]]
+    assert info_fast.n_levels <= 18 < info_ref.n_levels
 
 
 def test_fast_recording_is_shallow(Graph):
