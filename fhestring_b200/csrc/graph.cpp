@@ -239,6 +239,22 @@ Char Graph::trivial_char(uint8_t v) {
 
 Char Graph::flag_char(BlockId b) { return Char{b, trivial_block(0), trivial_block(0), trivial_block(0)}; }
 
+std::pair<BlockId, BlockId> Graph::differs_and_strict(const Char& a, const Char& b, bool greater) {
+    BlockId p[2];
+    {
+        SignedScope sc(signed_ok);
+        for (int j = 0; j < 2; j++)
+            p[j] = pbs({{a[2 * j], 1}, {a[2 * j + 1], 4}, {b[2 * j], -1}, {b[2 * j + 1], -4}}, 0,
+                       table_of([](int v) { return v != 0; }));
+    }
+    // 4 (hi + 1) + (lo + 1) with hi, lo in {0 smaller, 1 equal, 2 greater}; the high nibble decides unless it is equal
+    auto order = [](int v) { const int hi = v >> 2, lo = v & 3; return (hi == 1) ? lo : hi; };
+    const BlockId d = pbs({{p[1], 4}, {p[0], 1}}, 5, table_of([order](int v) { return (int)(order(v) != 1); }));
+    const int want = greater ? 2 : 0;
+    const BlockId s = pbs({{p[1], 4}, {p[0], 1}}, 5, table_of([order, want](int v) { return (int)(order(v) == want); }));
+    return {d, s};
+}
+
 Char Graph::eq(const Char& a, const Char& b) {
     std::vector<std::pair<BlockId, int>> s;
     for (int i = 0; i < 4; i++) s.push_back({bivar(a[i], b[i], [](int x, int y) { return x == y; }), 1});

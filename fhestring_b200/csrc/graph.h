@@ -108,6 +108,9 @@ public:
     Char or_of_ands(const std::vector<std::vector<BlockId>>& windows);  // OR_w AND_i flags[w][i], depth-minimised
     // generalisation of sum_flags: exact sum of 0/1 blocks as `ndigits` clean base-4 digits (little endian)
     std::vector<BlockId> sum_digits(const std::vector<BlockId>& flags, int ndigits);
+    // (a != b, a strictly greater (greater = true) or smaller than b) as two 0/1 blocks off the same packed-pair
+    // comparison the reference's recipe uses (cmp): 2 + 2 PBS per char pair
+    std::pair<BlockId, BlockId> differs_and_strict(const Char& a, const Char& b, bool greater);
     BlockId cond_bit(const Char& c);                  // c != 0 as a 0/1 block (scalar_ne(c, 0))
     Char flag_char(BlockId b);                        // BooleanBlock::into_radix: [b, 0, 0, 0]
     BlockId not_flag(BlockId b);                      // 1 - b, leveled

@@ -450,9 +450,20 @@ bool StringOps::find(const Str& s, const Str& pattern, Char& out) {
 
 Char StringOps::eq(const Str& s, const Str& o) {
     const size_t n = std::min(s.size(), o.size());
+    if (fast && s.size() <= 255 && o.size() <= 255) {
+        // (s_i == 0 && o_i == 0) || s_i == o_i  is just s_i == o_i.  With equal prefixes the two lengths (counts of
+        // non-NUL chars, no u8 wrap below 256 chars) differ exactly when the longer buffer's tail holds a non-NUL char,
+        // so "lengths equal" is "the tail is all NUL" and joins the same AND: no length is computed at all
+        std::vector<std::pair<Char, Char>> pairs;
+        for (size_t i = 0; i < n; i++) pairs.push_back({s[i], o[i]});
+        std::vector<Char> flags;
+        for (auto b : g.nibble_eq_flags(pairs)) flags.push_back(g.flag_char(b));
+        const Str& longer = s.size() > o.size() ? s : o;
+        for (size_t i = n; i < longer.size(); i++) flags.push_back(g.flag_char(g.not_flag(g.cond_bit(g.nonzero(longer[i])))));
+        return g.and_all(flags);
+    }
     const Char len1 = len(s), len2 = len(o);
     if (fast) {
-        // (s_i == 0 && o_i == 0) || s_i == o_i  is just s_i == o_i; the length test joins the same AND
         std::vector<std::pair<Char, Char>> pairs;
         for (size_t i = 0; i < n; i++) pairs.push_back({s[i], o[i]});
         pairs.push_back({len1, len2});
@@ -542,6 +553,69 @@ Char StringOps::comparison(const Str& s_in, const Str& o_in, int op) {
     Str s = s_in, o = o_in;
     size_t n = std::min(s.size(), o.size());
     if (n == 0) { s.push_back(zero()); o.push_back(zero()); n = 1; }
+    if (fast && s.size() <= 255 && o.size() <= 255 && n <= 15 * 15) {
+        // ret = comparison at the first differing index; without one, the length comparison decides.
+        //  * per char ONE packed-pair comparison gives d_i (differs) and t_i (differs in the op's direction; at a
+        //    differing index ge is gt and le is lt);
+        //  * "t_i and no earlier difference" is one first-in PBS inside a chunk of 15 chars, and at most one of them
+        //    is set per chunk, so their plain sum is the chunk's verdict; the same form ranks the chunks;
+        //  * with equal prefixes the lengths (no u8 wrap below 256 chars) compare like "the longer buffer's tail
+        //    holds a non-NUL char", a constant when both buffers have the same size.
+        const bool greater = op >= 2;
+        auto is_zero_tab = std::array<uint8_t, 16>{};
+        is_zero_tab[0] = 1;
+        std::array<uint8_t, 16> nz_tab{};
+        for (int v = 1; v < 16; v++) nz_tab[v] = 1;
+        std::vector<BlockId> d(n), t(n);
+        for (size_t i = 0; i < n; i++) std::tie(d[i], t[i]) = g.differs_and_strict(s[i], o[i], greater);
+        std::vector<BlockId> chunk_any, chunk_verdict;
+        for (size_t c0 = 0; c0 < n; c0 += 15) {
+            const size_t hi = std::min(n, c0 + 15);
+            std::vector<std::pair<BlockId, int>> firsts, diffs;
+            for (size_t i = c0; i < hi; i++) {
+                std::vector<std::pair<BlockId, int>> ops;
+                for (size_t k = c0; k < i; k++) ops.push_back({d[k], 1});
+                ops.push_back({t[i], -1});
+                firsts.push_back({i == c0 ? t[i] : g.pbs(ops, 1, is_zero_tab), 1});
+                diffs.push_back({d[i], 1});
+            }
+            chunk_verdict.push_back(g.lin(firsts, 0, 0x3));
+            chunk_any.push_back(diffs.size() == 1 ? diffs[0].first : g.pbs(diffs, 0, nz_tab));
+        }
+        std::vector<std::pair<BlockId, int>> verdicts, anys;
+        for (size_t c = 0; c < chunk_any.size(); c++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t k = 0; k < c; k++) ops.push_back({chunk_any[k], 1});
+            ops.push_back({chunk_verdict[c], -1});
+            // chunk 0 has no earlier chunk; with several chunks its 15-term sum is refreshed to one flag (same level as
+            // the others' first-in PBS), so the noise of the final sum stays at one unit per chunk
+            if (c == 0) verdicts.push_back({chunk_any.size() > 1 ? g.pbs({{chunk_verdict[0], 1}}, 0, nz_tab) : chunk_verdict[0], 1});
+            else verdicts.push_back({g.pbs(ops, 1, is_zero_tab), 1});
+            anys.push_back({chunk_any[c], 1});
+        }
+        const BlockId at_first = g.lin(verdicts, 0, 0x3);
+        const BlockId any = anys.size() == 1 ? anys[0].first : g.pbs(anys, 0, nz_tab);
+        // length comparison with equal prefixes: len1 - len2 = +/- (non-NUL chars in the longer buffer's tail)
+        BlockId by_len;
+        if (s.size() == o.size()) by_len = g.trivial_block((op == 1 || op == 3) ? 1 : 0);
+        else {
+            const bool s_longer = s.size() > o.size();
+            const Str& longer = s_longer ? s : o;
+            std::vector<Char> tail;
+            for (size_t i = n; i < longer.size(); i++) tail.push_back(g.nonzero(longer[i]));
+            const BlockId T = g.or_all(tail)[0];
+            // s longer: ge 1, gt T, le !T, lt 0;   o longer: le 1, lt T, ge !T, gt 0
+            const int as_s_longer[4] = {0 /*lt*/, 2 /*le: !T*/, 1 /*gt: T*/, 3 /*ge: 1*/};
+            const int as_o_longer[4] = {1 /*lt: T*/, 3 /*le: 1*/, 0 /*gt*/, 2 /*ge: !T*/};
+            const int kind = s_longer ? as_s_longer[op] : as_o_longer[op];
+            by_len = kind == 0 ? g.trivial_block(0) : kind == 3 ? g.trivial_block(1) : kind == 1 ? T : g.not_flag(T);
+        }
+        // at_first implies any, so a = at_first + any is 0 (no difference: the lengths decide), 1 (first difference
+        // against the op) or 2 (for it); x = a + 3 by_len keeps the weights, hence the noise, small
+        std::array<uint8_t, 16> fin{};
+        for (int v = 0; v < 6; v++) { const int a = v % 3, b = v / 3; fin[v] = (uint8_t)(a == 0 ? b : (a == 2)); }
+        return g.flag_char(g.pbs({{at_first, 1}, {any, 1}, {by_len, 3}}, 0, fin));
+    }
     const Char len1 = len(s), len2 = len(o);
     if (fast) {
         // ret = comparison at the first differing index; without one, the length comparison decides

@@ -259,6 +259,49 @@ def test_fast_split_scan_is_shallow(Graph):
     assert info_fast.n_levels <= 18 < info_ref.n_levels
 
 
+def test_eq_and_comparisons_random_buffers(Graph):
+    """== != < <= > >= on buffers of different sizes, equal prefixes, embedded NULs and non-NUL tails: the shallow
+    recordings (no length computation; first difference and direction in one first-in PBS) against the oracle"""
+    rng = random.Random(91)
+    levels = {}
+    for _ in range(220):
+        m = rng.choice(["eq", "ne", "lt", "le", "gt", "ge", "eq_ignore_case"])
+        la = rng.choice([0, 1, 2, 5, 14, 15, 16, 17, 31, 40])
+        ea = [rng.choice([0, 65, 66, 97, 98, 200, 255]) if rng.random() < 0.15 else rng.choice([65, 66, 97, 98]) for _ in range(la)]
+        mode = rng.random()
+        if mode < 0.3:
+            eb = list(ea)
+        elif mode < 0.5:
+            eb = list(ea[:rng.randrange(0, la + 1)])
+        elif mode < 0.7 and la:
+            k = rng.randrange(0, la)
+            eb = ea[:k] + [rng.choice([65, 66, 97, 98, 0])] + ea[k + 1:]
+        elif mode < 0.85:
+            eb = ea + [rng.choice([65, 66, 0]) for _ in range(rng.randrange(1, 4))]
+        else:
+            eb = [rng.choice([65, 66, 97, 98]) for _ in range(rng.randrange(0, 20))]
+        if rng.random() < 0.5:
+            ea, eb = eb, ea
+        ea, eb = ea + [0] * rng.randrange(0, 4), eb + [0] * rng.randrange(0, 4)
+        ref = oracle_raw(m, [ea, eb])
+        got, info = run_method(Graph, m, [ea, eb], 1)
+        assert int(got) == int(ref), (m, ea, eb)
+        levels[m] = max(levels.get(m, 0), info.n_levels)
+    assert levels["eq"] <= 3 and levels["ne"] <= 3 and max(levels[k] for k in ("lt", "le", "gt", "ge")) <= 5, levels
+    # config 3's shape: two 65-char buffers
+    s = [rng.randrange(32, 127) for _ in range(64)] + [0]
+    o = list(s)
+    o[40] = 33 if s[40] != 33 else 34
+    for m, fn in (("eq", P.eq), ("ge", P.ge), ("le", P.le)):
+        got, info = run_method(Graph, m, [s, o], 1)
+        assert int(got) == int(fn(s, o)) and info.n_levels <= (3 if m == "eq" else 5), (m, info.n_levels)
+    # above 255 chars the u8 length of the reference can wrap: those sizes keep the length-based recording
+    big = [97] * 257
+    for m, fn in (("eq", P.eq), ("ge", P.ge)):
+        got, _ = run_method(Graph, m, [big, big[:3]], 1)
+        assert int(got) == int(fn(big, big[:3])), m
+
+
 def test_fast_recording_is_shallow(Graph):
     """the point of the re-association: config 4 (contains over 257 chars, 8-char pattern) in a handful of levels"""
     rng = random.Random(4)
