@@ -27,7 +27,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple[str, ...] = ()) -> str:
     """variant="tag" with defines=("NAME=VALUE", ...) builds an experimental kernel variant (the FHESTR_BR_* switches
     of br_core.cuh) as libfhestr_engine_<tag>.so next to the default library; select it with FHESTR_ENGINE_LIB for
-    A/B runs (scripts/r1_ab_gpu_call.sh)."""
+    A/B runs (scripts/ab_variants_gpu.sh)."""
     objdir = os.path.join(HERE, f"build_{variant}" if variant else "build")
     lib = os.path.join(HERE, f"libfhestr_engine_{variant}.so") if variant else LIB
     flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
