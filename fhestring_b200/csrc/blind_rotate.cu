@@ -52,6 +52,9 @@ struct DevCtx {
     __device__ __forceinline__ void pair_sync() {
         asm volatile("bar.sync %0, 64;" ::"r"(slot_ + 1) : "memory");
     }
+    __device__ __forceinline__ void prefetch_l1(const cplx* p) const {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
     __device__ __forceinline__ cplx ldg(const cplx* p) const {
         const double2 v = __ldg(reinterpret_cast<const double2*>(p));
         return cplx{v.x, v.y};

@@ -38,6 +38,10 @@
 //       0 = the first round-1 kernel (also the only form with 2 or 4 PBS per CTA).
 //   FHESTR_BR_CVT_FP64=4 (default)  every 4th torus conversion of the epilogue runs on the FP64 pipe, see below.
 //   FHESTR_BR_PREFETCH=8, FHESTR_BR_I2F_FP64=0: measured, no gain beyond noise.
+//   FHESTR_BR_L1PF=0: NOT MEASURED YET (round-2 candidate).  1 = the key rows of a half-step that are not prefetched
+//       into registers are requested into L1 ahead of the pair barrier (prefetch.global.L1, no registers): the two
+//       FMAs that wait longest in the product stage wait on exactly those words coming from L2
+//       (profiles/r1_br_stall_breakdown.md).
 #ifndef FHESTR_BR_SLIM
 #define FHESTR_BR_SLIM 1
 #endif
@@ -59,6 +63,9 @@ constexpr int kPbsBaseLog = 23;
 constexpr int kBskPrefetch = FHESTR_BR_PREFETCH;    // key rows per half-step requested ahead of the pair barrier (8 = 64 registers)
 // FHESTR_BR_CVT_FP64 = m > 0: every m-th torus conversion of the epilogue runs on the FP64 pipe (four FP64 instructions,
 // bit-identical to the F2I) instead of the conversion unit, which sustains one F2I.S64 per 8 cycles per sub-partition
+#ifndef FHESTR_BR_L1PF
+#define FHESTR_BR_L1PF 0
+#endif
 #ifndef FHESTR_BR_CVT_FP64
 #define FHESTR_BR_CVT_FP64 4
 #endif
@@ -262,6 +269,13 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
             gsv[q] = c.ldg(g + bsk_index(p, half * 16 + q, p, t));
             gov[q] = c.ldg(g + bsk_index(1 - p, half * 16 + q, p, t));
         }
+#if FHESTR_BR_L1PF
+#pragma unroll
+        for (int q = kBskPrefetch; q < 16; q++) {
+            c.prefetch_l1(g + bsk_index(p, half * 16 + q, p, t));
+            c.prefetch_l1(g + bsk_index(1 - p, half * 16 + q, p, t));
+        }
+#endif
         c.pair_sync();
 #pragma unroll
         for (int q = 0; q < 16; q++) {

@@ -28,6 +28,7 @@ struct HostCtx {
     void syncwarp() { warp_bar->arrive_and_wait(); }
     void pair_sync() { pair_bar->arrive_and_wait(); }
     cplx ldg(const cplx* p) const { return *p; }
+    void prefetch_l1(const cplx*) const {}
     // slim variant: word ((x >> 2) mod N) of this polynomial's accumulator, negated when bit 13 of the byte offset is set
     acc_t acc_ld_rot(uint32_t x) const {
         const acc_t v = acc_[(x >> 2) & (kN - 1)];
