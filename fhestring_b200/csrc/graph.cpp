@@ -154,7 +154,11 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     std::vector<std::pair<BlockId, int>> ops = ops_in;
     const uint32_t S = vset_of(ops, cst);
     if (S >> 16 & 1) fail("PBS input can reach the ambiguous value 16");
-    if (!signed_ok && (S >> 16)) fail("PBS input overflows into the padding bit");
+    if (!signed_ok && (S >> 16)) {
+        std::string m = "PBS input overflows into the padding bit:";
+        for (auto& op : ops) m += " (" + std::to_string(op.second) + " x vset " + std::to_string(nodes[op.first].vset) + ")";
+        fail(m + " + " + std::to_string(cst));
+    }
     // image of the value set; padding-bit inputs give -f(v-16)
     uint32_t O = 0;
     for (int v = 0; v < 32; v++) {
@@ -570,6 +574,79 @@ Char Graph::add_disjoint(const std::vector<Char>& parts) {
 // with two bivariate LUTs per carried block.  z_i comes from chunked prefix counts: an exact base count per
 // chunk of 13 (sum_digits over the flag prefix, shared through CSE) plus the local count (<= 12, leveled),
 // normalised by one carry chain.
+// The routing layers of compact_nonzero for long strings, at about half the PBS (throughput matters there, depth does
+// not).  Per layer only the MOVING part of a block is a PBS,  mv_i = (bit of the control digit y_i) ? x_i : 0  on
+// x_i + 4 y_i; the staying part is the plain difference, so  x'_i = x_i - mv_i + mv_(i+sh)  is leveled.  The price is
+// noise: x' gains two units per layer, so it carries weight 1 in the PBS input, the control digit weight 4 and the digit
+// has to be a fresh PBS output: a digit is refreshed when it becomes the active one, routed between its two layers by
+// ONE PBS on 4 y_i + y_(i+sh), and while it waits it is routed like the data.  Blocks are refreshed when their noise
+// would no longer fit next to the control digit.  PBS per position at 1025 chars: 161 -> about 90.
+std::vector<Char> Graph::route_linear(const std::vector<Char>& s, std::vector<std::vector<BlockId>> ctrl, int B, int nd) {
+    const size_t L = s.size();
+    std::vector<Char> cur = s;
+    const BlockId zero = trivial_block(0);
+    auto is_zero = [&](BlockId b) { return is_trivial(b) && trivial_value(b) == 0; };
+    auto fresh_enough = [&](BlockId b) { return is_trivial(b) || nodes[b].noise2 + 16.f <= kNoise2Limit; };
+    for (int b = 0; b < B; b++) {
+        const size_t sh = (size_t)1 << b;
+        const int kb = b / 2, bit = b & 1;
+        auto move_tab = table_of([bit](int v) { return (((v >> 2) >> bit) & 1) ? (v & 3) : 0; });
+        // the active digit as a fresh PBS output (digit 0 starts fresh; an odd layer gets it from the one-PBS routing below)
+        std::vector<BlockId> y(L);
+        for (size_t i = 0; i < L; i++) {
+            BlockId d = ctrl[i][kb];
+            if (!is_trivial(d) && (nodes[d].kind == BKind::Linear || nodes[d].noise2 > 1.f)) d = refresh(d);
+            y[i] = d;
+        }
+        auto moving = [&](BlockId x, size_t i) {   // the part of x that leaves position i in this layer
+            if (is_zero(x) || is_zero(y[i])) return zero;
+            if (is_trivial(y[i])) return ((trivial_value(y[i]) >> bit) & 1) ? x : zero;
+            if (is_trivial(x)) { const int cx = trivial_value(x); return pbs({{y[i], 1}}, 0, table_of([bit, cx](int v) { return ((v >> bit) & 1) ? cx : 0; })); }
+            return pbs({{x, 1}, {y[i], 4}}, 0, move_tab);
+        };
+        auto routed = [&](BlockId x_here, BlockId mv_here, BlockId x_in, BlockId mv_in) {
+            uint32_t vs = 1u | (nodes[x_here].vset & 0xF);
+            std::vector<std::pair<BlockId, int>> ops{{x_here, 1}, {mv_here, -1}};
+            if (!is_zero(mv_in)) { ops.push_back({mv_in, 1}); vs |= nodes[x_in].vset & 0xF; }
+            return lin(ops, 0, vs);
+        };
+        std::vector<Char> mvd(L);
+        std::vector<std::vector<BlockId>> mvc(L, std::vector<BlockId>(nd, zero));
+        for (size_t i = 0; i < L; i++) {
+            for (int q = 0; q < 4; q++) {
+                if (!fresh_enough(cur[i][q])) cur[i][q] = refresh(cur[i][q]);
+                mvd[i][q] = moving(cur[i][q], i);
+            }
+            for (int d = kb + 1; d < nd; d++) {
+                if (!fresh_enough(ctrl[i][d])) ctrl[i][d] = refresh(ctrl[i][d]);
+                mvc[i][d] = moving(ctrl[i][d], i);
+            }
+        }
+        std::vector<Char> nxt(L);
+        std::vector<std::vector<BlockId>> nctrl(L, std::vector<BlockId>(nd, zero));
+        for (size_t i = 0; i < L; i++) {
+            const bool has_in = i + sh < L;
+            for (int q = 0; q < 4; q++)
+                nxt[i][q] = routed(cur[i][q], mvd[i][q], has_in ? cur[i + sh][q] : zero, has_in ? mvd[i + sh][q] : zero);
+            for (int d = kb + 1; d < nd; d++)
+                nctrl[i][d] = routed(ctrl[i][d], mvc[i][d], has_in ? ctrl[i + sh][d] : zero, has_in ? mvc[i + sh][d] : zero);
+            if (bit == 0) {   // the active digit is needed once more: stays unless its own bit 0 is set, the incoming one moves if its bit 0 is set
+                const BlockId a = y[i], c = has_in ? y[i + sh] : zero;
+                auto stay_v = [](int v) { return (v & 1) ? 0 : v; };
+                auto move_v = [](int v) { return (v & 1) ? v : 0; };
+                if (is_trivial(a) && is_trivial(c)) nctrl[i][kb] = trivial_block(stay_v(trivial_value(a)) + move_v(trivial_value(c)));
+                else if (is_trivial(c)) { const int cc = move_v(trivial_value(c)); nctrl[i][kb] = pbs({{a, 1}}, 0, table_of([=](int v) { return stay_v(v & 3) + cc; })); }
+                else if (is_trivial(a)) { const int ca = stay_v(trivial_value(a)); nctrl[i][kb] = pbs({{c, 1}}, 0, table_of([=](int v) { return ca + move_v(v & 3); })); }
+                // (both non-zero cannot happen in a compaction: two elements would collide; & 3 keeps the value set a digit)
+                else nctrl[i][kb] = pbs({{a, 4}, {c, 1}}, 0, table_of([=](int v) { return (stay_v(v >> 2) + move_v(v & 3)) & 3; }));
+            }
+        }
+        cur.swap(nxt);
+        ctrl.swap(nctrl);
+    }
+    return cur;
+}
+
 std::vector<Char> Graph::compact_nonzero(const std::vector<Char>& s) {
     const size_t L = s.size();
     if (L <= 1) return s;
@@ -600,6 +677,7 @@ std::vector<Char> Graph::compact_nonzero(const std::vector<Char>& s) {
             }
         }
     }
+    if (L > kLinearRoutingMinLength) return route_linear(s, ctrl, B, nd);
     std::vector<Char> cur = s;
     for (int b = 0; b < B; b++) {
         const size_t sh = (size_t)1 << b;

@@ -159,6 +159,8 @@ private:
     bool signed_ok = false;
     void fail(const std::string& m) { if (error.empty()) error = m; }
     Char cmp(const Char& a, const Char& b, int op);
+    static constexpr size_t kLinearRoutingMinLength = 64;   // longer strings: half the PBS per routing layer, more levels
+    std::vector<Char> route_linear(const std::vector<Char>& s, std::vector<std::vector<BlockId>> ctrl, int B, int nd);
     std::array<BlockId, 4> propagate(std::array<BlockId, 4> s);
 };
 
