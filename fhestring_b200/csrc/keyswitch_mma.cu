@@ -31,7 +31,7 @@ __device__ __forceinline__ int swz(int row, int chunk) { return row * kGemmBK + 
 
 // ---- kernel 1: digits.  One CTA per ciphertext.
 __global__ void __launch_bounds__(256) ks_digits_kernel(KsBatchArgs A) {
-    extern __shared__ __align__(16) unsigned char sm[];
+    extern __shared__ __align__(128) unsigned char sm[];
     const int b = blockIdx.x;
     const fhestr_job& j = A.jobs[b];
     const int level = A.level, base_log = A.base_log;
