@@ -239,6 +239,20 @@ def contains_leg(eng, ck, stream, rank, world, steps, barrier):
     return out
 
 
+def _hbm_side(traffic_bytes, ms_per_launch):
+    """DRAM traffic of one blind-rotation launch (ncu) over its duration, against MEASURED_PEAKS.json's hbm_gbs"""
+    if not traffic_bytes or ms_per_launch <= 0:
+        return None
+    peak, src = 7700.0, "nominal HBM3e"
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    achieved = traffic_bytes / (ms_per_launch * 1e-3) / 1e9
+    return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": src}
+
+
 def reference_arm(args, out):
     """--impl reference: the reference's own CPU implementation is tfhe-rs (Rust, not buildable here: no
     cargo, crate not vendored), so this times the oracle port of the same f64-FFT algorithm."""
@@ -432,6 +446,8 @@ def main():
                                "MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s",
                 "keyswitch_ms_per_launch": ks_ms / max(1, br_launches),
                 "kernel_share_of_step": br_ms / ms_total,
+                # why the bound is FP64 and not HBM: the same kernel against the measured copy bandwidth
+                "hbm": _hbm_side(165.4e6 if B == BATCH else None, br_avg_ms),
             },
             "e2e": {"value": e2e_value, "unit": "PBS/s", "h2d_bytes_per_step": int(B * 2049 * 8),
                     "d2h_bytes_per_step": int(B * 2049 * 8), "ms_per_step": e2e_ms / args.steps},
