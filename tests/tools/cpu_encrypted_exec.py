@@ -3,7 +3,7 @@ blind rotation stands in for the GPU kernels (same algorithm, same noise), level
 to check new graph recordings for noise, not only for value: the phase error of every PBS INPUT is measured against the
 decoding margin (delta/2 = 2^58), which the plaintext interpretation (plain_exec.py) cannot see.
 
-  python tests/tools/cpu_encrypted_exec.py ge 65 | eq 65 | compact 65 | split hello ello | rsplitn hello l 2
+  python tests/tools/cpu_encrypted_exec.py ge 65 | eq 65 | compact 65 | split hello ello | rsplitn hello l 2 | replace hello ello _llo | contains STRING PATTERN
 About 22 PBS/s per host core, so keep programs to a few thousand PBS."""
 from __future__ import annotations
 
@@ -89,6 +89,12 @@ def main():
         add(a); add(b)
         rs, rc = g.string_op(what, ids, fast=True)
         outs = [rc]
+    elif what in ("replace", "contains", "find"):
+        add([ord(c) for c in sys.argv[2]] + [0])
+        for extra in sys.argv[3:]:
+            add([ord(c) for c in extra])
+        rs, rc = g.string_op(what, ids, fast=True)
+        outs = (list(rs) if rs is not None else []) + ([rc] if rc is not None else [])
     elif what == "compact":
         L = int(sys.argv[2])
         s = [int(x) if rng.random() < 0.6 else 0 for x in rng.integers(1, 256, L)]
