@@ -422,6 +422,86 @@ bool StringOps::rfind(const Str& s_in, const Str& pattern, Char& out) {
     return true;
 }
 
+// find over more than 15 windows (at most 255, so at most 17 chunks of 15): index of the first matching window, 255 if
+// none.  Inside a chunk "match and no earlier match" is one first-in PBS per window; the chunks are ranked the same way
+// on their ANY flags (the 16th and 17th chunk through one OR of the first fifteen); a result digit is then
+//     sum_d d * [ some chunk c is the first one AND its first window has digit d ]
+// where the inner flag is one PBS on  h_c + (sum of the chunk's first-in flags whose index has that digit)  -- the sum
+// is 0/1 because at most one of them is set -- and the OR over the chunks is again an exclusive sum, cleaned by one PBS.
+// Eight levels where the one-hot over all windows followed by two levels of class ORs took ten.
+Char StringOps::first_index_fast(const Str& s, const Str& pattern, size_t windows) {
+    std::array<uint8_t, 16> is_zero_tab{}, nz_tab{}, is2_tab{};
+    is_zero_tab[0] = 1;
+    is2_tab[2] = 1;
+    for (int v = 1; v < 16; v++) nz_tab[v] = 1;
+    std::vector<BlockId> m(windows);
+    for (size_t w = 0; w < windows; w++) m[w] = g.cond_bit(match_at(s, w, pattern, true));
+    const size_t C = (windows + 14) / 15;
+    std::vector<BlockId> fm(windows), any(C), h(C);
+    for (size_t c = 0; c < C; c++) {
+        const size_t lo = 15 * c, hi = std::min(windows, lo + 15);
+        std::vector<std::pair<BlockId, int>> all;
+        for (size_t w = lo; w < hi; w++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t k = lo; k < w; k++) ops.push_back({m[k], 1});
+            ops.push_back({m[w], -1});
+            fm[w] = w == lo ? m[w] : g.pbs(ops, 1, is_zero_tab);
+            all.push_back({m[w], 1});
+        }
+        any[c] = all.size() == 1 ? all[0].first : g.pbs(all, 0, nz_tab);
+    }
+    // rank the chunks
+    BlockId overall;
+    {
+        const size_t direct = std::min<size_t>(C, 15);
+        std::vector<std::pair<BlockId, int>> head;
+        for (size_t c = 0; c < direct; c++) {
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t k = 0; k < c; k++) ops.push_back({any[k], 1});
+            ops.push_back({any[c], -1});
+            h[c] = c == 0 ? any[0] : g.pbs(ops, 1, is_zero_tab);
+            head.push_back({any[c], 1});
+        }
+        BlockId pre = head.size() == 1 ? head[0].first : g.pbs(head, 0, nz_tab);   // OR of the first fifteen
+        std::vector<std::pair<BlockId, int>> seen{{pre, 1}};
+        for (size_t c = direct; c < C; c++) {
+            std::vector<std::pair<BlockId, int>> ops = seen;
+            ops.push_back({any[c], -1});
+            h[c] = g.pbs(ops, 1, is_zero_tab);
+            seen.push_back({any[c], 1});
+        }
+        overall = seen.size() == 1 ? pre : g.pbs(seen, 0, nz_tab);
+    }
+    const BlockId none = g.not_flag(overall);
+    Char r;
+    for (int q = 0; q < 4; q++) {
+        std::vector<std::pair<BlockId, int>> digit_ops;
+        for (int d = 1; d <= 3; d++) {
+            std::vector<std::pair<BlockId, int>> lo_half, hi_half;   // two partial sums: a leveled job takes 16 terms
+            for (size_t c = 0; c < C; c++) {
+                std::vector<std::pair<BlockId, int>> cls;
+                for (size_t w = 15 * c; w < std::min(windows, 15 * c + 15); w++)
+                    if ((int)((w >> (2 * q)) & 3) == d) cls.push_back({fm[w], 1});
+                if (cls.empty()) continue;
+                const BlockId in_chunk = g.lin(cls, 0, 0x3);
+                if (g.is_trivial(in_chunk) && g.trivial_value(in_chunk) == 0) continue;
+                const BlockId hit = g.pbs({{h[c], 1}, {in_chunk, 1}}, 0, is2_tab);
+                (c < 9 ? lo_half : hi_half).push_back({hit, 1});
+            }
+            if (((kMaxFindLength >> (2 * q)) & 3) == (size_t)d) hi_half.push_back({none, 1});
+            std::vector<std::pair<BlockId, int>> both;
+            if (!lo_half.empty()) both.push_back({g.lin(lo_half, 0, 0x3), 1});
+            if (!hi_half.empty()) both.push_back({g.lin(hi_half, 0, 0x3), 1});
+            if (both.empty()) continue;
+            const BlockId sum = g.lin(both, 0, 0x3);
+            const size_t n_terms = lo_half.size() + hi_half.size();
+            digit_ops.push_back({n_terms == 1 ? sum : g.pbs({{sum, 1}}, 0, nz_tab), d});
+        }
+        r[q] = g.lin(digit_ops, 0, 0xF);
+    }
+    return r;
+}
+
 bool StringOps::find(const Str& s, const Str& pattern, Char& out) {
     if (s.empty() && pattern.empty()) { out = zero(); return true; }
     if (s.size() >= kMaxFindLength + pattern.size()) {
@@ -430,6 +510,10 @@ bool StringOps::find(const Str& s, const Str& pattern, Char& out) {
     }
     if (pattern.size() > s.size()) { out = g.trivial_char(255); return true; }
     const size_t end = s.size() - pattern.size();
+    if (fast && end + 1 > 15) {
+        out = first_index_fast(s, pattern, end + 1);
+        return true;
+    }
     if (fast) {
         std::vector<Char> m;
         std::vector<uint8_t> values;

@@ -312,7 +312,7 @@ def test_fast_recording_is_shallow(Graph):
     assert info_fast.n_levels <= 6 and info_fast.n_pbs < 10000
     got_find, info_find = run_method(Graph, "find", [s, pat], 1)
     assert got_find == 124 == P.find(s, pat)
-    assert info_find.n_levels <= 10
+    assert info_find.n_levels <= 8
     s2 = list(s)
     s2[130] = 65
     assert run_method(Graph, "contains", [s2, pat], 1)[0] == 0
