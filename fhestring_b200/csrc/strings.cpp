@@ -406,6 +406,12 @@ bool StringOps::rfind(const Str& s_in, const Str& pattern, Char& out) {
     }
     if (pattern.size() > s.size()) { out = g.trivial_char(255); return true; }
     const size_t end = adjust_end_of_pattern(s.size() - pattern.size());
+    if (fast && end > 15) {
+        std::vector<BlockId> m;
+        for (size_t w = 0; w < end; w++) m.push_back(g.cond_bit(match_at(s, w, pattern, false)));
+        out = first_index_fast(m, true);
+        return true;
+    }
     if (fast) {
         std::vector<Char> m;
         std::vector<uint8_t> values;
@@ -422,20 +428,24 @@ bool StringOps::rfind(const Str& s_in, const Str& pattern, Char& out) {
     return true;
 }
 
-// find over more than 15 windows (at most 255, so at most 17 chunks of 15): index of the first matching window, 255 if
-// none.  Inside a chunk "match and no earlier match" is one first-in PBS per window; the chunks are ranked the same way
+// find / rfind over more than 15 windows (at most 255, so at most 17 chunks of 15): index of the first (last) set flag,
+// 255 if none.  Inside a chunk "match and no earlier match" is one first-in PBS per window; the chunks are ranked the same way
 // on their ANY flags (the 16th and 17th chunk through one OR of the first fifteen); a result digit is then
 //     sum_d d * [ some chunk c is the first one AND its first window has digit d ]
 // where the inner flag is one PBS on  h_c + (sum of the chunk's first-in flags whose index has that digit)  -- the sum
 // is 0/1 because at most one of them is set -- and the OR over the chunks is again an exclusive sum, cleaned by one PBS.
 // Eight levels where the one-hot over all windows followed by two levels of class ORs took ten.
-Char StringOps::first_index_fast(const Str& s, const Str& pattern, size_t windows) {
+Char StringOps::first_index_fast(const std::vector<BlockId>& flags, bool last) {
     std::array<uint8_t, 16> is_zero_tab{}, nz_tab{}, is2_tab{};
     is_zero_tab[0] = 1;
     is2_tab[2] = 1;
     for (int v = 1; v < 16; v++) nz_tab[v] = 1;
+    const size_t windows = flags.size();
+    // position k of the ranking order is window index_of[k]: ascending for the first match, descending for the last
+    std::vector<size_t> index_of(windows);
+    for (size_t k = 0; k < windows; k++) index_of[k] = last ? windows - 1 - k : k;
     std::vector<BlockId> m(windows);
-    for (size_t w = 0; w < windows; w++) m[w] = g.cond_bit(match_at(s, w, pattern, true));
+    for (size_t k = 0; k < windows; k++) m[k] = flags[index_of[k]];
     const size_t C = (windows + 14) / 15;
     std::vector<BlockId> fm(windows), any(C), h(C);
     for (size_t c = 0; c < C; c++) {
@@ -481,7 +491,7 @@ Char StringOps::first_index_fast(const Str& s, const Str& pattern, size_t window
             for (size_t c = 0; c < C; c++) {
                 std::vector<std::pair<BlockId, int>> cls;
                 for (size_t w = 15 * c; w < std::min(windows, 15 * c + 15); w++)
-                    if ((int)((w >> (2 * q)) & 3) == d) cls.push_back({fm[w], 1});
+                    if ((int)((index_of[w] >> (2 * q)) & 3) == d) cls.push_back({fm[w], 1});
                 if (cls.empty()) continue;
                 const BlockId in_chunk = g.lin(cls, 0, 0x3);
                 if (g.is_trivial(in_chunk) && g.trivial_value(in_chunk) == 0) continue;
@@ -511,7 +521,9 @@ bool StringOps::find(const Str& s, const Str& pattern, Char& out) {
     if (pattern.size() > s.size()) { out = g.trivial_char(255); return true; }
     const size_t end = s.size() - pattern.size();
     if (fast && end + 1 > 15) {
-        out = first_index_fast(s, pattern, end + 1);
+        std::vector<BlockId> m;
+        for (size_t w = 0; w <= end; w++) m.push_back(g.cond_bit(match_at(s, w, pattern, true)));
+        out = first_index_fast(m, false);
         return true;
     }
     if (fast) {

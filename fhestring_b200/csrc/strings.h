@@ -73,7 +73,7 @@ private:
     Str handle_longer_from(const Str& bytes, const Str& from, Str to, const Char& n, bool use_counter);
     Str handle_shorter_from(const Str& bytes, const Str& from, const Str& to, const Char& n, bool use_counter);
     std::vector<Char> last_one_hot(const std::vector<Char>& flags, Char* any);
-    Char first_index_fast(const Str& s, const Str& pattern, size_t windows);   // find over 16..255 windows, 8 levels
+    Char first_index_fast(const std::vector<BlockId>& flags, bool last);   // find / rfind over 16..255 windows, 8 levels
     Char is_not_blank(const Char& c);
     Char is_blank_not_nul(const Char& c);
     Char rsplit_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);   // split.rs:10
