@@ -604,7 +604,7 @@ StripResult StringOps::strip_suffix(const Str& s_in, const Str& needle) {
     Str s = s_in;
     if (needle.size() > s.size()) return StripResult{s, zero()};
     const size_t end = s.size() - needle.size();
-    if (fast && s.size() <= 255) {
+    if (fast && end < 255) {   // window indices stay below the reference's "none" sentinel 255 (pos is a u8)
         std::vector<Char> all_nonzero, match;
         for (size_t i = 0; i <= end; i++) {
             std::vector<Char> nz;
