@@ -929,6 +929,37 @@ void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& resul
     }
 }
 
+// Column t of the split buffers: buffer j takes `src` iff the number of set flags in `seen` -- capped at *cap in the
+// n forms -- equals j.  Up to 15 distinct flags and no cap: "count == j" is ONE PBS on the flag sum per buffer;
+// otherwise the count is formed as a u8 (sum_flags), capped, and compared with j.
+void StringOps::copy_to_counted_buffer(const std::vector<Char>& seen, const Char* cap, const Char& src, size_t t,
+                                       std::vector<Str>& result) {
+    const size_t size = result.size();
+    std::vector<std::pair<BlockId, int>> live;
+    for (auto& c : seen) if (!(g.is_trivial(c[0]) && g.trivial_value(c[0]) == 0)) live.push_back({c[0], 1});
+    bool repeats = false;   // a shared node would be summed with a coefficient > 1
+    for (size_t a = 0; a < live.size() && !repeats; a++)
+        for (size_t b = a + 1; b < live.size(); b++) if (live[a].first == live[b].first) { repeats = true; break; }
+    if (!cap && live.size() <= 15 && !repeats) {
+        for (size_t j = 0; j < size && j <= live.size(); j++) {
+            std::array<uint8_t, 16> tab{};
+            tab[j & 15] = 1;
+            const BlockId hit = live.empty() ? g.trivial_block(j == 0 ? 1 : 0) : g.pbs(live, 0, tab);
+            result[j][t] = g.mul_flag_char(hit, src);
+        }
+        return;
+    }
+    Char ccb = g.sum_flags(seen);
+    if (cap) {
+        const BlockId capped = g.cond_bit(g.ge(ccb, *cap));
+        ccb = g.add_disjoint({g.mul_flag_char(capped, *cap), g.mul_flag_char(g.not_flag(capped), ccb)});
+    }
+    for (size_t j = 0; j < size; j++) {
+        const BlockId hit = g.cond_bit(g.block_and_eq({{g.trivial_char((uint8_t)(j & 255)), ccb}}));
+        result[j][t] = g.mul_flag_char(hit, src);
+    }
+}
+
 // Depth-minimised scan of _split / _rsplit (split.rs:883-988, :307-393), plaintext-identical to the serial one:
 //  * the raw window matches come from the ORIGINAL string and are independent;
 //  * the `ignore` bookkeeping of the reference only ever blocks a match because of an EARLIER match whose marked range
@@ -1002,30 +1033,7 @@ SplitResult StringOps::split_scan_fast(const Str& s, const Str& pattern, const C
     for (size_t tt = 0; tt < size; tt++) {
         const size_t t = reverse ? size - 1 - tt : tt;
         const Char src = n ? g.mul_flag_char(allow, s[t]) : s[t];
-        std::vector<std::pair<BlockId, int>> live;
-        for (auto& c : seen) if (!(g.is_trivial(c[0]) && g.trivial_value(c[0]) == 0)) live.push_back({c[0], 1});
-        bool repeats = false;
-        for (size_t a = 0; a < live.size() && !repeats; a++)
-            for (size_t b = a + 1; b < live.size(); b++) if (live[a].first == live[b].first) { repeats = true; break; }
-        if (!n && live.size() <= 15 && !repeats) {
-            // ccb == j is one PBS on the sum of the flags seen so far
-            for (size_t j = 0; j < size && j <= live.size(); j++) {
-                std::array<uint8_t, 16> tab{};
-                tab[j & 15] = 1;
-                const BlockId hit = live.empty() ? (j == 0 ? f1 : f0) : g.pbs(live, 0, tab);
-                result[j][t] = g.mul_flag_char(hit, src);
-            }
-        } else {
-            Char ccb = g.sum_flags(seen);
-            if (n) {
-                const BlockId capped = g.cond_bit(g.ge(ccb, cap));
-                ccb = g.add_disjoint({g.mul_flag_char(capped, cap), g.mul_flag_char(g.not_flag(capped), ccb)});
-            }
-            for (size_t j = 0; j < size; j++) {
-                const BlockId hit = g.cond_bit(g.block_and_eq({{g.trivial_char((uint8_t)(j & 255)), ccb}}));
-                result[j][t] = g.mul_flag_char(hit, src);
-            }
-        }
+        copy_to_counted_buffer(seen, n ? &cap : nullptr, src, t, result);
         seen.push_back(g.flag_char(found[t]));
     }
     std::vector<Char> any;
@@ -1101,22 +1109,7 @@ SplitResult StringOps::split_ascii_whitespace(const Str& s) {
         for (size_t i = 0; i < size; i++) {
             seen.push_back(g.flag_char(inc[i]));
             const Char src = g.mul_flag_char(g.not_flag(ws[i]), s[i]);
-            std::vector<std::pair<BlockId, int>> live;
-            for (auto& c : seen) if (!(g.is_trivial(c[0]) && g.trivial_value(c[0]) == 0)) live.push_back({c[0], 1});
-            if (live.size() <= 15) {
-                for (size_t j = 0; j < size && j <= live.size(); j++) {
-                    std::array<uint8_t, 16> tab{};
-                    tab[j & 15] = 1;
-                    const BlockId hit = live.empty() ? g.trivial_block(j == 0 ? 1 : 0) : g.pbs(live, 0, tab);
-                    result[j][i] = g.mul_flag_char(hit, src);
-                }
-            } else {
-                const Char ccb = g.sum_flags(seen);
-                for (size_t j = 0; j < size; j++) {
-                    const BlockId hit = g.cond_bit(g.block_and_eq({{g.trivial_char((uint8_t)(j & 255)), ccb}}));
-                    result[j][i] = g.mul_flag_char(hit, src);
-                }
-            }
+            copy_to_counted_buffer(seen, nullptr, src, i, result);
         }
         for (size_t j = 0; j < size; j++) result[j] = bubble_zeroes_right(result[j]);
         std::vector<Char> any;

@@ -80,6 +80,7 @@ private:
     Char split_pattern_matching(size_t i, const Str& s, const Str& pattern, Str& ignore);    // split.rs:70
     void copy_logic(size_t i, const Char* n, const Str& s, std::vector<Str>& result, const Char& allow, const Char& ccb);  // :108
     void handle_n_case(const Char& found, const Char* n, Char& ccb, Char& stop);              // split.rs:137
+    void copy_to_counted_buffer(const std::vector<Char>& seen, const Char* cap, const Char& src, size_t t, std::vector<Str>& result);
     SplitResult split_scan_fast(const Str& s, const Str& pattern, const Char* n, bool reverse);   // parallel form of the scans of :307 / :883
     void clear_pattern_from_result(const Char* n, std::vector<Str>& result, const Str& pattern, bool inclusive, bool terminator);  // :180
 };
