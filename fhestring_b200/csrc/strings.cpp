@@ -930,8 +930,8 @@ void StringOps::clear_pattern_from_result(const Char* n, std::vector<Str>& resul
 }
 
 // Column t of the split buffers: buffer j takes `src` iff the number of set flags in `seen` -- capped at *cap in the
-// n forms -- equals j.  Up to 15 distinct flags and no cap: "count == j" is ONE PBS on the flag sum per buffer;
-// otherwise the count is formed as a u8 (sum_flags), capped, and compared with j.
+// n forms -- equals j.  Up to 15 distinct flags and no (or a clear) cap: "count == j" is ONE PBS on the flag sum per
+// buffer; otherwise the count is formed as a u8 (sum_flags), capped, and compared with j.
 void StringOps::copy_to_counted_buffer(const std::vector<Char>& seen, const Char* cap, const Char& src, size_t t,
                                        std::vector<Str>& result) {
     const size_t size = result.size();
@@ -940,10 +940,20 @@ void StringOps::copy_to_counted_buffer(const std::vector<Char>& seen, const Char
     bool repeats = false;   // a shared node would be summed with a coefficient > 1
     for (size_t a = 0; a < live.size() && !repeats; a++)
         for (size_t b = a + 1; b < live.size(); b++) if (live[a].first == live[b].first) { repeats = true; break; }
-    if (!cap && live.size() <= 15 && !repeats) {
+    // a clear cap (rsplit_once: n = 2; the *_clear forms) keeps the one-PBS form: buffer j < cap takes count == j,
+    // buffer cap takes count >= cap, later buffers nothing
+    int clear_cap = -1;
+    if (cap) {
+        bool triv = true;
+        for (int q = 0; q < 4; q++) triv = triv && g.is_trivial((*cap)[q]);
+        if (triv) { clear_cap = 0; for (int q = 0; q < 4; q++) clear_cap |= (g.trivial_value((*cap)[q]) & 3) << (2 * q); }
+    }
+    if ((!cap || clear_cap >= 0) && live.size() <= 15 && !repeats) {
         for (size_t j = 0; j < size && j <= live.size(); j++) {
+            if (clear_cap >= 0 && (int)j > clear_cap) break;
             std::array<uint8_t, 16> tab{};
-            tab[j & 15] = 1;
+            if (clear_cap >= 0 && (int)j == clear_cap) { for (int v = (int)j; v < 16; v++) tab[v] = 1; }
+            else tab[j & 15] = 1;
             const BlockId hit = live.empty() ? g.trivial_block(j == 0 ? 1 : 0) : g.pbs(live, 0, tab);
             result[j][t] = g.mul_flag_char(hit, src);
         }

@@ -250,6 +250,38 @@ def test_split_family_random_cases(Graph):
     assert checked == 140
 
 
+def test_splitn_with_a_clear_n(Graph):
+    """splitn / rsplitn with n given in the clear (the CLI's *_clear forms, rsplit_once): the copy buffer index is
+    decoded by one PBS per buffer with the cap folded into the table"""
+    from plain_exec import blocks_of, run_program
+    rng = random.Random(31)
+    for _ in range(60):
+        m = rng.choice(["splitn", "rsplitn"])
+        s = "".join(rng.choice("ab. ") for _ in range(rng.randrange(0, 9)))
+        pat = rng.choice(["", ".", "a", "aa", "ab", " ", "b."])
+        n = rng.choice([0, 1, 2, 3, 4, 7, 17, 255])
+        es, ep = [ord(c) for c in s] + [0] * rng.randrange(0, 3), [ord(c) for c in pat]
+        g = Graph()
+        slots, vals, ids = [], [], []
+        for arr in (es, ep):
+            i, sl = g.input_chars(len(arr))
+            ids.append(i); slots.append(sl.reshape(-1)); vals.append(blocks_of(arr).reshape(-1))
+        ids.append(g.trivial_chars([n]))
+        bufs, found = g.split_op(m, ids, fast=True)
+        g.mark_output([x for b in bufs for x in b] + [found])
+        g.compile(1)
+        plain = run_program(g, np.concatenate(slots), np.concatenate(vals))
+
+        def char_val(cid):
+            sl = g.char_slots([cid])[0]
+            return sum(int(plain[int(sl[q])] % 16 & 3) << (2 * q) for q in range(4))
+
+        got = [[char_val(c) for c in b] for b in bufs]
+        ref = (P._split if m == "splitn" else P._rsplit)(list(es), list(ep), False, False, n)
+        assert got == [list(b) for b in ref[0]] and char_val(found) == int(ref[1]), (m, s, pat, n)
+        g.close()
+
+
 def test_fast_split_scan_is_shallow(Graph):
     """the depth-minimised scan: one level per position instead of four (the reference's op order: 29 levels)"""
     enc = encode_args("split", ["hello", "ello"], 1)
