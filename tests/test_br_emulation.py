@@ -16,6 +16,7 @@ VARIANTS = {
     "default": (),   # aligned accumulator + every 4th torus conversion on the FP64 pipe
     "first_r1_kernel": ("FHESTR_BR_SLIM=0", "FHESTR_BR_CVT_FP64=0"),
     "all_fp64_conversions": ("FHESTR_BR_CVT_FP64=1", "FHESTR_BR_I2F_FP64=1"),
+    "l1_prefetch_and_depth_12": ("FHESTR_BR_L1PF=1", "FHESTR_BR_PREFETCH=12"),
 }
 
 
