@@ -7,7 +7,6 @@
 // each polynomial on an 8 KiB-aligned shared address: 5 KiB of padding behind the mask) and one padded transpose
 // matrix per warp (2 x 8448 B) = 40 448 B: 4 CTAs (+ 1 KiB reserved each) still fit the 164 KB carve-out, which
 // leaves 92 KB of L1 for the twiddle tables and the BSK tile the 4 CTAs of an SM read at nearly the same time.
-// (FHESTR_BR_SLIM=0 is the unaligned 35 328 B layout of the first round-1 kernel.)
 // The Fourier BSK (46 MiB for n = 742) stays resident in the 126 MB L2 and is read with 16-byte
 // read-only loads, one 64 KiB step tile per CMUX.
 #include "kernels.cuh"
@@ -16,8 +15,7 @@ namespace fhestr {
 
 constexpr int kAtildeBytes = 2048;  // up to 1024 u16
 constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
-[[maybe_unused]] constexpr int kPairSmemBytes = kAccBytes + 2 * kWarpXbufDoubles * 8 + kAtildeBytes;  // 35 328 B
-#if FHESTR_BR_SLIM
+static_assert(FHESTR_BR_SLIM == 1, "the unaligned-accumulator layout of the first round-1 kernel is gone from the tree");
 // aligned layout (one PBS per CTA only): [mask 2 KiB][pad][acc0 8 KiB | acc1 8 KiB, each on an 8 KiB-aligned SHARED
 // address][two transpose matrices].  The CTA's shared window starts at 0x400 (1 KiB is reserved per CTA), so the
 // pad is 5 KiB: 40 448 B per CTA, and 4 x (40 448 + 1 024) = 162 KiB still fits the 164 KiB carve-out.  The kernel
@@ -25,7 +23,6 @@ constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomi
 constexpr int kSlimSharedBase = 0x400;
 constexpr int kSlimPad = (8192 - ((kSlimSharedBase + kAtildeBytes) & 8191)) & 8191;
 constexpr int kSlimSmemBytes = kAtildeBytes + kSlimPad + kAccBytes + 2 * kWarpXbufDoubles * 8;  // 40 448 B
-#endif
 
 struct DevCtx {
     int lane_, poly_, slot_;
@@ -33,7 +30,6 @@ struct DevCtx {
     double* xbuf_;
     double* xbuf_partner_;
     uint16_t* atilde_;
-#if FHESTR_BR_SLIM
     uint32_t acc_s_;   // shared-space address of this polynomial's accumulator, 8 KiB aligned
     // word ((x >> 2) mod N) of the accumulator, negated when bit 13 of the byte offset x is set (negacyclic wrap)
     __device__ __forceinline__ acc_t acc_ld_rot(uint32_t x) const {
@@ -41,7 +37,6 @@ struct DevCtx {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(acc_s_ | (x & 0x1ffcu)) : "memory");
         return (x & 0x2000u) ? 0u - v : v;
     }
-#endif
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ int poly() const { return poly_; }
     __device__ __forceinline__ acc_t* acc() { return acc_; }
@@ -73,8 +68,7 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     c.lane_ = threadIdx.x & 31;
     c.poly_ = warp & 1;
     c.slot_ = slot;
-#if FHESTR_BR_SLIM
-    static_assert(P == 1, "the slim variant is one PBS per CTA");
+    static_assert(P == 1, "one PBS per CTA");
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t pad = (8192u - ((s0 + kAtildeBytes) & 8191u)) & 8191u;
     uint32_t dyn;
@@ -86,13 +80,6 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     c.acc_ = acc + c.poly_ * kN;
     c.acc_s_ = s0 + kAtildeBytes + pad + c.poly_ * kN * (uint32_t)sizeof(acc_t);
     c.atilde_ = reinterpret_cast<uint16_t*>(smem);
-#else
-    unsigned char* base = smem + (size_t)slot * kPairSmemBytes;
-    acc_t* acc = reinterpret_cast<acc_t*>(base);
-    double* xb = reinterpret_cast<double*>(base + kAccBytes);
-    c.acc_ = acc + c.poly_ * kN;
-    c.atilde_ = reinterpret_cast<uint16_t*>(base + kAccBytes + 2 * kWarpXbufDoubles * 8);
-#endif
     c.xbuf_ = xb + c.poly_ * kWarpXbufDoubles;
     c.xbuf_partner_ = xb + (1 - c.poly_) * kWarpXbufDoubles;
 
@@ -111,44 +98,17 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     br_thread_main(c, job, A.bsk, A.tf, A.ti);
 }
 
-#if FHESTR_BR_SLIM
 cudaError_t blind_rotate_configure() {
     return cudaFuncSetAttribute(blind_rotate_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlimSmemBytes);
 }
-#else
-template <int P, int MB>
-static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<P, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, P * kPairSmemBytes);
-}
 
-cudaError_t blind_rotate_configure() {
-    cudaError_t e;
-    if ((e = configure_one<1, 4>()) != cudaSuccess) return e;
-    if ((e = configure_one<2, 2>()) != cudaSuccess) return e;
-    return configure_one<4, 1>();
-}
-#endif
-
-// pbs_per_cta: 0 = default (1); 2 and 4 exist only in FHESTR_BR_SLIM=0 builds (the default build runs 1).  Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255
-// registers is the fastest shape; independent CTAs drift out of phase and overlap their FP64 and shared-memory
-// phases, while 2 or 4 PBS per CTA run in lockstep (1.3-1.5x slower), and sizing the register allocation for
-// 5-6 CTAs per SM (168 registers) makes every warp ~1.6x slower for 1.5x the warps (net 0.8x).
-int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s) {
+// Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255 registers is the fastest shape; independent
+// CTAs drift out of phase and overlap their FP64 and shared-memory phases, while 2 or 4 PBS per CTA ran in lockstep
+// (1.3-1.5x slower), and sizing the register allocation for 5-6 CTAs per SM (168 registers) made every warp ~1.6x
+// slower for 1.5x the warps (net 0.8x).  Those variants are gone from the tree (git history: round 1).
+int launch_blind_rotate(const BrBatchArgs& a, cudaStream_t s) {
     if (a.B <= 0) return 0;
-#if FHESTR_BR_SLIM
-    (void)pbs_per_cta;
     blind_rotate_kernel<1, 4><<<a.B, 64, kSlimSmemBytes, s>>>(a);
-#else
-    int P = pbs_per_cta;
-    if (P != 1 && P != 2 && P != 4) P = 1;
-    const int grid = (a.B + P - 1) / P;
-    const int smem = P * kPairSmemBytes;
-    switch (P) {
-        case 1: blind_rotate_kernel<1, 4><<<grid, 64, smem, s>>>(a); break;
-        case 2: blind_rotate_kernel<2, 2><<<grid, 128, smem, s>>>(a); break;
-        default: blind_rotate_kernel<4, 1><<<grid, 256, smem, s>>>(a); break;
-    }
-#endif
     return 1;
 }
 

@@ -33,9 +33,9 @@ struct fhestr_engine {
     int ks_path = 0;                   // 0 = tensor cores (IMMA), 1 = CUDA cores (u64 IMAD)
     cplx* tf = nullptr;
     cplx* ti = nullptr;
-    cplx* bsk_q = nullptr;     // the four-warp kernel's layout of the same key
-    cplx* qtab = nullptr;      // tq [1024] | tqt [1024] | w64 [64]
-    QuadTables qt{};
+    cplx* bsk_w = nullptr;     // the same key in the spectrum order of the latency kernel (br_wide.cuh)
+    WideConsts* wide_tab = nullptr;   // [kWT] per-thread transform constants of the latency kernel
+    int n_sms = 148;
     bool keys_loaded = false;
     u64* luts = nullptr;
     int n_luts = 0, cap_luts = 256;
@@ -47,7 +47,8 @@ struct fhestr_engine {
     size_t ks_cap = 0;
     uint8_t* d_bytes = nullptr;
     size_t bytes_cap = 0;
-    int pbs_per_cta = 0;
+    int br_mode = 0;                   // 0 = by level size, 1 = throughput kernel only, 2 = latency kernel only
+    int wide_max_jobs = 0;             // levels of at most this many PBS jobs run on the latency kernel (0 = 2 x SMs)
     uint64_t launches = 0;
     bool timing = false;
     struct Timed { cudaEvent_t a, b, c; uint32_t pbs; };   // a..b keyswitch, b..c blind rotation
@@ -213,16 +214,16 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
         CKC(cudaMemcpyAsync(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
         CKC(cudaStreamSynchronize(e->stream));
     }
-    CKC(cudaMalloc(&e->qtab, (1024 + 1024 + 64) * sizeof(cplx)));
+    e->n_sms = prop.multiProcessorCount;
+    CKC(cudaMalloc(&e->wide_tab, kWT * sizeof(WideConsts)));
     {
-        std::vector<cplx> t(1024 + 1024 + 64);
-        make_quad_tables(t.data(), t.data() + 1024, t.data() + 2048);
-        CKC(cudaMemcpyAsync(e->qtab, t.data(), t.size() * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
+        std::vector<WideConsts> t(kWT);
+        make_wide_consts(t.data());
+        CKC(cudaMemcpyAsync(e->wide_tab, t.data(), t.size() * sizeof(WideConsts), cudaMemcpyHostToDevice, e->stream));
         CKC(cudaStreamSynchronize(e->stream));
-        e->qt = QuadTables{e->qtab, e->qtab + 1024, e->qtab + 2048};
     }
-    CKC(cudaMalloc(&e->bsk_q, (size_t)p->n * kQBskStepElems * sizeof(cplx)));
-    CKC(blind_rotate_quad_configure());
+    CKC(cudaMalloc(&e->bsk_w, (size_t)p->n * kWKeyTile * sizeof(cplx)));
+    CKC(blind_rotate_wide_configure());
     CKC(cudaMalloc(&e->luts, (size_t)e->cap_luts * kN * sizeof(u64)));
     CKC(cudaMalloc(&e->bsk_f, (size_t)p->n * kBskStepElems * sizeof(cplx)));
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
@@ -247,7 +248,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     cudaFree(e->my_flags);
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
-    cudaFree(e->bsk_q); cudaFree(e->qtab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
+    cudaFree(e->bsk_w); cudaFree(e->wide_tab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
     cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -278,7 +279,7 @@ int fhestr_load_keys(fhestr_engine* e, const uint64_t* bsk_std, const uint64_t* 
     CK(cudaMemcpyAsync(d_std, bsk_std, bsk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->ksk, ksk, ksk_words * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
     e->launches += launch_bsk_convert(d_std, p.n, e->tf, e->bsk_f, e->stream);
-    e->launches += launch_bsk_convert_quad(d_std, p.n, e->qt, e->bsk_q, e->stream);
+    e->launches += launch_bsk_convert_wide(d_std, p.n, e->wide_tab, e->bsk_w, e->stream);
     e->launches += launch_ksk_correction(e->ksk, kN * p.ks_level, p.n, p.ks_base_log, e->ksk_corr, e->stream);
     e->launches += launch_ksk_limbs(e->ksk, kN * p.ks_level, p.n, e->ksk8, e->stream);
     CK(cudaGetLastError());
@@ -359,6 +360,16 @@ int fhestr_ct_trivial(fhestr_engine* e, uint32_t first, uint32_t count, const ui
     return FHESTR_OK;
 }
 
+// Which blind-rotation kernel runs a level: a level with few jobs is bound by the serial chain of 742 CMUX steps of ONE
+// PBS, so it runs on the latency kernel (one PBS per SM, 128 threads, br_wide.cuh); a level with many jobs is bound by
+// FP64 issue and runs on the throughput kernel (four PBS per SM, br_core.cuh).
+static bool use_wide(const fhestr_engine* e, uint32_t n_pbs) {
+    if (e->br_mode == 1) return false;
+    if (e->br_mode == 2) return true;
+    const uint32_t lim = e->wide_max_jobs > 0 ? (uint32_t)e->wide_max_jobs : 2u * (uint32_t)e->n_sms;
+    return n_pbs <= lim;
+}
+
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
 static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all, bool peer_stores = false) {
     if (n_pbs) {
@@ -375,12 +386,12 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
         br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
-        br.bsk_q = e->bsk_q; br.qt = e->qt;
+        br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
         br.n_peers = 0;
         if (e->peers_attached && peer_stores) {
             for (uint32_t r = 0; r < e->world; r++) if (r != e->rank) br.peer_arena[br.n_peers++] = e->peer_arena[r];
         }
-        e->launches += (e->pbs_per_cta == 8 && !br.n_peers) ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+        e->launches += use_wide(e, n_pbs) ? launch_blind_rotate_wide(br, e->stream) : launch_blind_rotate(br, e->stream);
         if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
@@ -666,8 +677,8 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
     br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = d_ids; br.jobs = nullptr; br.arena = e->arena;
     br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.init_acc = d_init; br.out_acc = d_out;
     br.n = e->prm.n; br.B = (int)count;
-    br.bsk_q = e->bsk_q; br.qt = e->qt;
-    e->launches += e->pbs_per_cta == 8 ? launch_blind_rotate_quad(br, e->stream) : launch_blind_rotate(br, e->pbs_per_cta, e->stream);
+    br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
+    e->launches += use_wide(e, count) ? launch_blind_rotate_wide(br, e->stream) : launch_blind_rotate(br, e->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc_out_host, d_out, acc_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -746,9 +757,10 @@ int fhestr_set_keyswitch_path(fhestr_engine* e, int path) {
     return FHESTR_OK;
 }
 
-int fhestr_set_pbs_per_cta(fhestr_engine* e, int v) {
-    if (!e || (v != 0 && v != 1 && v != 2 && v != 4 && v != 8)) return FHESTR_E_INVALID;
-    e->pbs_per_cta = v;
+int fhestr_set_br_mode(fhestr_engine* e, int mode, int wide_max_jobs) {
+    if (!e || mode < 0 || mode > 2 || wide_max_jobs < 0) return FHESTR_E_INVALID;
+    e->br_mode = mode;
+    e->wide_max_jobs = wide_max_jobs;
     return FHESTR_OK;
 }
 

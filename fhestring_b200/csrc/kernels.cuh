@@ -5,7 +5,7 @@
 
 #include "../../include/fhestr_engine.h"
 #include "br_core.cuh"
-#include "br_quad.cuh"
+#include "br_wide.cuh"
 
 namespace fhestr {
 
@@ -22,8 +22,8 @@ struct BrBatchArgs {
     u64* out_acc;             // optional [B][2][N]
     u64* peer_arena[7];       // arenas of the other ranks (cudaIpc-mapped), n_peers of them
     int n_peers;
-    const cplx* bsk_q;        // Fourier BSK, layout of the four-warp kernel (br_quad.cuh)
-    QuadTables qt;
+    const cplx* bsk_w;        // Fourier BSK in the spectrum order of the latency kernel (br_wide.cuh), [n][kWKeyTile]
+    const WideConsts* wide_tab;   // [kWT] per-thread transform constants of the latency kernel
     int n;
     int B;
 };
@@ -43,13 +43,13 @@ struct KsBatchArgs {
 
 // K0+K1: linear combination + LWE keyswitch.  Returns the number of kernels launched.
 int launch_keyswitch(const KsBatchArgs& a, cudaStream_t s);
-// K2+K3+K4: mod-switch + blind rotation + sample extract.  pbs_per_cta in {0 (auto), 1, 2, 4}.
-int launch_blind_rotate(const BrBatchArgs& a, int pbs_per_cta, cudaStream_t s);
+// K2+K3+K4: mod-switch + blind rotation + sample extract, throughput form (one PBS per pair of warps, br_core.cuh)
+int launch_blind_rotate(const BrBatchArgs& a, cudaStream_t s);
 cudaError_t blind_rotate_configure();
-// the same, four warps per PBS (br_quad.cuh)
-int launch_blind_rotate_quad(const BrBatchArgs& a, cudaStream_t s);
-cudaError_t blind_rotate_quad_configure();
-int launch_bsk_convert_quad(const u64* bsk_std, int n, const QuadTables& tb, cplx* out, cudaStream_t s);
+// the same in its latency form: one PBS per 128-thread CTA, one CTA per SM, key tiles by bulk TMA (br_wide.cuh)
+int launch_blind_rotate_wide(const BrBatchArgs& a, cudaStream_t s);
+cudaError_t blind_rotate_wide_configure();
+int launch_bsk_convert_wide(const u64* bsk_std, int n, const WideConsts* tab, cplx* out, cudaStream_t s);
 cudaError_t keyswitch_configure();  // opt in to the large dynamic shared memory carve-out
 // the same on the tensor cores (IMMA u8 x u8 -> s32 limb-split GEMM); bit-identical results
 int launch_keyswitch_mma(const KsBatchArgs& a, cudaStream_t s);

@@ -146,8 +146,9 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self.lib.fhestr_kernel_launches(self.h))
 
-    def set_pbs_per_cta(self, v: int):
-        self._ck(self.lib.fhestr_set_pbs_per_cta(self.h, C.c_int(v)))
+    def set_br_mode(self, mode: int, wide_max_jobs: int = 0):
+        """0 = kernel by level size (default), 1 = throughput kernel only, 2 = latency kernel only"""
+        self._ck(self.lib.fhestr_set_br_mode(self.h, C.c_int(mode), C.c_int(wide_max_jobs)))
 
     def set_keyswitch_path(self, path: int):
         """0 = tensor cores (IMMA limb-split GEMM, default), 1 = CUDA cores"""

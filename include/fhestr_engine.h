@@ -225,10 +225,12 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
 int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_mhz_hint);
 /* number of kernels this engine has launched so far (bench.py's gpu_launches) */
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
-/* blind-rotation launch shape override for experiments: PBS per CTA (0 = automatic = 1); 8 selects the
- * four-warps-per-PBS kernel (br_quad.cuh); 2 and 4 (measured 1.3-1.5x slower) exist only in a library built with
- * -DFHESTR_BR_SLIM=0 and run as 1 otherwise */
-int fhestr_set_pbs_per_cta(fhestr_engine* e, int pbs_per_cta);
+/* Which blind-rotation kernel runs a level.  mode 0 (default): by level size -- levels of at most wide_max_jobs PBS
+ * jobs (0 = twice the SM count) run on the latency kernel (one PBS per SM over 128 threads, key tiles by bulk TMA),
+ * larger ones on the throughput kernel (four PBS per SM).  mode 1 / 2 force the throughput / latency kernel (tests,
+ * measurements).  Both kernels compute the same function; their outputs are different valid ciphertexts of the same
+ * plaintext (two f64 FFT orders), see DESIGN.md. */
+int fhestr_set_br_mode(fhestr_engine* e, int mode, int wide_max_jobs);
 /* keyswitch implementation: 0 = tensor cores (u8 limb-split IMMA GEMM, default), 1 = CUDA cores (u64 IMAD);
  * both are exact and produce identical words */
 int fhestr_set_keyswitch_path(fhestr_engine* e, int path);

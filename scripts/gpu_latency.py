@@ -1,5 +1,8 @@
-"""Latency of one dependency level vs its size, for both blind-rotation kernels (shape 1 = one warp per
-polynomial, shape 8 = two warps per polynomial).  usage: python scripts/gpu_latency.py"""
+"""Latency of ONE dependency level against its size, for both blind-rotation kernels (throughput: one PBS per pair of
+warps, four per SM; latency: one PBS per 128-thread CTA, one per SM, key tiles by bulk TMA).  The crossover sets the
+engine's default level-size threshold (fhestr_set_br_mode).  usage: python scripts/gpu_latency.py [sizes...]
+Writes gpurun_out/level_latency.json."""
+import json
 import os
 import sys
 
@@ -13,7 +16,7 @@ from fhestring_b200.engine import Engine, single_term_jobs  # noqa: E402
 
 ck = ClientKey(seed=1)
 bsk, ksk = ck.server_keys()
-BMAX = 4736
+BMAX = 1184
 eng = Engine(arena_blocks=2 * BMAX + 8)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
@@ -22,13 +25,13 @@ eng.load_keys(bsk, ksk)
 vals = np.random.default_rng(0).integers(0, 16, BMAX).astype(np.uint8)
 eng.upload(0, ck.encrypt_blocks(vals))
 ident = eng.lut(list(range(16)))
-for B in ([int(x) for x in sys.argv[1:]] or (1, 17, 148, 296, 592, 888, 1184, 2368, 4736)):
+rows = []
+for B in ([int(x) for x in sys.argv[1:]] or (1, 2, 16, 32, 74, 148, 149, 250, 296, 297, 444, 500, 592, 1184)):
     jobs = single_term_jobs(BMAX + np.arange(B), np.arange(B), ident)
     prog = eng.program(jobs, [0, B])
-    row = [f"B={B:5d}"]
-    for shape in (1,) if len(sys.argv) > 1 else (1, 9):
-        eng.set_pbs_per_cta(1)
-        eng.set_keyswitch_path(0 if shape == 1 else 1)
+    row = dict(jobs=B)
+    for mode, name in ((1, "throughput"), (2, "latency")):
+        eng.set_br_mode(mode)
         for _ in range(2):
             prog.run()
         torch.cuda.synchronize()
@@ -41,8 +44,13 @@ for B in ([int(x) for x in sys.argv[1:]] or (1, 17, 148, 296, 592, 888, 1184, 23
         torch.cuda.synchronize()
         ks_ms, br_ms, nl, npbs = eng.get_timing()
         eng.set_timing(False)
-        ok = np.array_equal(ck.decrypt_blocks(eng.download(BMAX, B)), vals[:B])
-        row.append(f"ks {'imma' if shape == 1 else 'imad'}: level {a.elapsed_time(b) / 3:7.3f} ms (ks {ks_ms / 3:6.3f}, br {br_ms / 3:7.3f}) ok={ok}")
-    print("  ".join(row), flush=True)
+        ok = bool(np.array_equal(ck.decrypt_blocks(eng.download(BMAX, B)), vals[:B]))
+        row[name] = dict(level_ms=round(a.elapsed_time(b) / 3, 4), keyswitch_ms=round(ks_ms / 3, 4),
+                         blind_rotate_ms=round(br_ms / 3, 4), decrypt_ok=ok)
+    rows.append(row)
+    print(json.dumps(row), flush=True)
     prog.close()
+eng.set_br_mode(0)
 eng.close()
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "level_latency.json"), "w"), indent=1)

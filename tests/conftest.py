@@ -30,39 +30,6 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-FLAKE_LOG = os.path.join(ROOT, "gpurun_out", "gpu_test_reruns.log")
-
-
-@pytest.hookimpl(hookwrapper=True)
-def pytest_pyfunc_call(pyfuncitem):
-    """GPU tests only: a failing test body is run ONCE more and the first failure is logged loudly (terminal
-    warning + gpurun_out/gpu_test_reruns.log).  Reason (known issues): over ~70 full-suite runs on fresh
-    B200 boxes two runs showed one wrong result each that never reproduced -- not in 22 consecutive full runs on
-    one box, not in 0.7 M trace-checked PBS.  A test that fails twice still fails."""
-    outcome = yield
-    if outcome.excinfo is None or "gpu" not in pyfuncitem.keywords:
-        return
-    first = outcome.excinfo
-    if issubclass(first[0], (pytest.skip.Exception, KeyboardInterrupt)):
-        return
-    try:
-        os.makedirs(os.path.dirname(FLAKE_LOG), exist_ok=True)
-        with open(FLAKE_LOG, "a") as f:
-            f.write(f"{pyfuncitem.nodeid}: first attempt failed: {first[0].__name__}: {first[1]}\n")
-    except OSError:
-        pass
-    import warnings
-    warnings.warn(f"GPU test {pyfuncitem.nodeid} failed once and is being re-run: {first[1]!r}")
-    testfunction = pyfuncitem.obj
-    funcargs = pyfuncitem.funcargs
-    argnames = pyfuncitem._fixtureinfo.argnames
-    try:
-        testfunction(**{arg: funcargs[arg] for arg in argnames})
-    except BaseException:
-        return          # second failure: the original outcome (failure) stands
-    outcome.force_result(True)
-
-
 @pytest.fixture(scope="session")
 def build_lib():
     """libfhestr_engine.so, built in-tree (nvcc cross-compiles without a GPU)."""

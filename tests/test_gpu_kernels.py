@@ -17,6 +17,17 @@ pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(ROOT, "tests", "golden", "pbs_small.npz"))
 
 
+def _record(kind, row):
+    """measured accuracy figures of a GPU run, one JSON line each (copied into profiles/ by hand)"""
+    import json
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "k3_accuracy.jsonl"), "a") as f:
+            f.write(json.dumps(dict(kind=kind, **row)) + "\n")
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="module")
 def small_engine(build_lib, small_oracle):
     from fhestring_b200.engine import Engine
@@ -126,11 +137,13 @@ def test_keyswitch_tensor_core_and_cuda_core_paths_identical(full_engine, full_o
     assert np.array_equal(a[:len(lin)], o.keyswitch(keys, lin))
 
 
-def test_single_external_product_tolerance(build_lib, small_oracle):
-    """K3 on one CMUX step with a random (worst-case, full-range) GLWE, vs exact integers + golden"""
+@pytest.mark.parametrize("br_mode", [1, 2], ids=["throughput_kernel", "latency_kernel"])
+def test_single_external_product_tolerance(build_lib, small_oracle, br_mode):
+    """K3 on one CMUX step with a random (worst-case, full-range) GLWE, vs exact integers + golden; both kernels"""
     from fhestring_b200.engine import Engine
     o, keys = small_oracle
     eng = Engine(arena_blocks=8, n=1)
+    eng.set_br_mode(br_mode)
     eng.load_keys(keys.bsk[:1], np.ascontiguousarray(keys.ksk[:, :, [0, SMALL_N]]))
     rng = np.random.default_rng(3)
     es = [1, 777, 2048, 2048 + 5, 4095, 0]
@@ -153,21 +166,23 @@ def test_single_external_product_tolerance(build_lib, small_oracle):
         want = o.external_product_exact(keys.bsk[0], diff, glwe[b])
         d = (got[b] - want).astype(np.int64).astype(float)
         if e == 0:
-            assert not d.any()  # skipped step: exactly the input
+            assert not d.any()  # nothing to add (the throughput kernel skips the step, the latency kernel adds 0)
             continue
         # RMS <= 2^-24, max <= 2^-21 of the torus (f64 FFT round-off + the 2^-33 rounding to acc_t)
         assert np.sqrt(np.mean(d * d)) <= 2.0**40, (e, np.log2(np.sqrt(np.mean(d * d))))
         assert np.abs(d).max() <= 2.0**43, (e, np.log2(np.abs(d).max()))
+        _record("external_product", dict(kernel=br_mode, e=e, log2_rms_torus=float(np.log2(np.sqrt(np.mean(d * d))) - 64),
+                                         log2_max_torus=float(np.log2(np.abs(d).max()) - 64)))
     eng.close()
 
 
-@pytest.mark.parametrize("pbs_per_cta", [0, 1, 2, 4, 8])
-def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, pbs_per_cta):
+@pytest.mark.parametrize("br_mode", [0, 1, 2], ids=["by_level_size", "throughput_kernel", "latency_kernel"])
+def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, br_mode):
     """K0..K4 end to end on 32 block values incl. the padding-bit half (negacyclic sign), several LUTs,
-    batch size not a multiple of the CTA tile, every launch shape"""
+    batch size not a multiple of the CTA tile, both blind-rotation kernels"""
     from fhestring_b200.engine import single_term_jobs
     o, keys = small_oracle
-    small_engine.set_pbs_per_cta(pbs_per_cta)
+    small_engine.set_br_mode(br_mode)
     vals = np.arange(32)
     small_engine.upload(0, o.encrypt_big(keys, vals, seed=21))
     tables = [list(range(16)), [(3 * x + 1) % 16 for x in range(16)], [int((x >> 2) == (x & 3)) for x in range(16)]]
@@ -179,7 +194,7 @@ def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, pbs_pe
     dec = o.decrypt_big(keys, small_engine.download(500, B))
     want = [(tables[i // 32][v % 16] * (1 if v < 16 else -1)) % 16 for i in range(B) for v in [i % 32]]
     assert np.array_equal(dec, np.array(want))
-    small_engine.set_pbs_per_cta(0)
+    small_engine.set_br_mode(0)
 
 
 def test_pbs_matches_oracle_exact_decryption_golden(small_engine, small_oracle):
@@ -255,12 +270,43 @@ def test_full_parameters_4096_blocks(full_engine, full_oracle):
     # to it (oracle f64 route: 5.9e-10 measured on 384 samples; this kernel: 8.4e-10).  What the
     # parameter set needs is var_pbs * 25 (max noise level 5) << var_ks + var_modswitch = 4.75e-6, i.e.
     # var_pbs << 1.9e-7; we hold the kernel to 1e-9 so that an accuracy regression is caught early.
+    _record("pbs_output_noise", dict(kernel=1, blocks=B, variance=float(np.var(err)), max_abs=float(np.abs(err).max())))
     assert np.var(err) <= 1.0e-9, np.var(err)
     assert np.abs(err).max() < 1.0 / 64
     # size-independent property: PBS with the identity LUT is idempotent on the decrypted value
     jobs2 = single_term_jobs(np.arange(B), B + np.arange(B), ident)
     full_engine.pbs_batch(jobs2)
     assert np.array_equal(o.decrypt_big(keys, full_engine.download(0, B)), want)
+
+
+def test_full_parameters_latency_kernel(full_engine, full_oracle):
+    """the latency kernel at the real parameters, 280 blocks (two waves of one CTA per SM): all decrypt correctly,
+    output noise variance as tight as the throughput kernel's, and the kernel choice by level size is the same call"""
+    from fhestring_b200.engine import single_term_jobs
+    o, keys = full_oracle
+    B = 280
+    rng = np.random.default_rng(12)
+    vals = rng.integers(0, 16, B)
+    full_engine.upload(0, o.encrypt_big(keys, vals, seed=19))
+    table = [(7 * x + 2) % 16 for x in range(16)]
+    jobs = single_term_jobs(4096 + np.arange(B), np.arange(B), full_engine.lut(table))
+    outs = {}
+    for mode in (2, 1, 0):
+        full_engine.set_br_mode(mode)
+        full_engine.pbs_batch(jobs)
+        outs[mode] = full_engine.download(4096, B)
+    full_engine.set_br_mode(0)
+    want = np.array([table[v] for v in vals])
+    for mode, out in outs.items():
+        assert np.array_equal(o.decrypt_big(keys, out), want), mode
+        err = (o.phases(keys.s_glwe, out).astype(np.int64) - (want.astype(np.int64) << 59)).astype(float) / 2.0**64
+        _record("pbs_output_noise", dict(kernel=mode, blocks=B, variance=float(np.var(err)), max_abs=float(np.abs(err).max())))
+        assert np.var(err) <= 1.0e-9, (mode, np.var(err))
+    # 280 <= 2 x SMs: mode 0 picked the latency kernel -> the very same words as mode 2
+    assert np.array_equal(outs[0], outs[2])
+    # both kernels are valid PBS of the same input: phases differ by the scheme's own rounding noise only
+    dp = (o.phases(keys.s_glwe, outs[1]) - o.phases(keys.s_glwe, outs[2])).astype(np.int64).astype(float) / 2.0**64
+    assert np.abs(dp).max() < 2.0**-11
 
 
 def test_full_parameters_phase_close_to_cpu_fft_route(full_engine, full_oracle):

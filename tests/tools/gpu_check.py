@@ -89,8 +89,8 @@ def full_checks(B=4096):
     jobs = single_term_jobs(B + np.arange(B), np.arange(B), ident)
     jobs["lut"][1::2] = eq
     tf, mhz = eng.measure_fp64_peak(); print("measured FP64 peak TFLOP/s", tf, "clock attr MHz", mhz)
-    for P in (1, 2, 4, 8):
-        eng.set_pbs_per_cta(P)
+    for P in (1, 2):
+        eng.set_br_mode(P)
         prog = eng.program(jobs, [0, B])
         for _ in range(2): prog.run()
         torch.cuda.synchronize()
