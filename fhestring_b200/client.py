@@ -24,7 +24,11 @@ def _u8p(a):
 class ClientKey:
     """MyClientKey::from_params (client_key.rs:30-35): secret keys + the server key material."""
 
-    def __init__(self, seed: int = 1, lwe_std: float = LWE_STD, glwe_std: float = GLWE_STD, **params):
+    def __init__(self, seed: int | None = None, lwe_std: float = LWE_STD, glwe_std: float = GLWE_STD, **params):
+        """seed=None (default): keys and all encryption randomness from OS entropy.  An explicit non-zero seed gives
+        reproducible keys and is for tests and benchmarks only."""
+        if seed is not None and int(seed) == 0:
+            raise ValueError("seed 0 is reserved (it means OS entropy at the C ABI); pass None for that")
         self.lib = load_library()
         prm = dict(PARAM_MESSAGE_2_CARRY_2_KS_PBS)
         prm.update(params)
@@ -33,7 +37,7 @@ class ClientKey:
         self.big = self.N + 1
         h = C.c_void_p()
         rc = self.lib.fhestr_client_create(C.byref(self.params), C.c_double(lwe_std), C.c_double(glwe_std),
-                                           C.c_uint64(seed), C.byref(h))
+                                           C.c_uint64(0 if seed is None else int(seed)), C.byref(h))
         if rc:
             raise EngineError(f"fhestr_client_create failed ({rc})")
         self.h = h

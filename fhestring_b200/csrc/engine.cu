@@ -126,6 +126,18 @@ static int fail(fhestr_engine* e, int code, const std::string& msg) {
     return code;
 }
 
+// After a synchronising call: a peer flag barrier that timed out (a peer died or fell behind by more than the spin
+// bound) leaves a non-zero status word; the results of that run are incomplete, so the call fails instead of
+// returning them.  The word stays set until fhestr_peer_detach.
+static int check_peer_status(fhestr_engine* e) {
+    if (!e->peers_attached || !e->my_flags) return FHESTR_OK;
+    uint32_t st = 0;
+    CK(cudaMemcpyAsync(&st, e->my_flags + 8, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (st) return fail(e, FHESTR_E_STATE, "a multi-GPU level barrier timed out: peer results are incomplete (fhestr_peer_status)");
+    return FHESTR_OK;
+}
+
 // Grow the per-batch scratch.  A failed allocation leaves the capacity at 0 and the pointers null, so the next call
 // allocates again instead of running on freed memory.
 static int ensure_scratch(fhestr_engine* e, size_t n_jobs) {
@@ -263,7 +275,7 @@ int fhestr_set_stream(fhestr_engine* e, void* cuda_stream) {
 int fhestr_sync(fhestr_engine* e) {
     if (!e) return FHESTR_E_INVALID;
     CK(cudaStreamSynchronize(e->stream));
-    return FHESTR_OK;
+    return check_peer_status(e);
 }
 
 void* fhestr_arena_ptr(fhestr_engine* e) { return e ? e->arena : nullptr; }
@@ -346,6 +358,14 @@ int fhestr_ct_download(fhestr_engine* e, uint32_t first, uint32_t count, uint64_
     CK(cudaMemcpyAsync(host, e->arena + (size_t)first * (kN + 1), (size_t)count * (kN + 1) * sizeof(u64),
                        cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return check_peer_status(e);
+}
+
+int fhestr_ct_download_async(fhestr_engine* e, uint32_t first, uint32_t count, uint64_t* pinned_host) {
+    if (!e || !pinned_host) return FHESTR_E_INVALID;
+    if ((uint64_t)first + count > e->arena_blocks) return fail(e, FHESTR_E_STATE, "download outside the arena");
+    CK(cudaMemcpyAsync(pinned_host, e->arena + (size_t)first * (kN + 1), (size_t)count * (kN + 1) * sizeof(u64),
+                       cudaMemcpyDeviceToHost, e->stream));
     return FHESTR_OK;
 }
 
@@ -480,6 +500,12 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
     if (rc) return rc;
     if (world > 1 && ((!e->comm && !e->peers_attached) || e->world != world || e->rank != rank))
         return fail(e, FHESTR_E_STATE, "multi-rank run needs fhestr_peer_attach or fhestr_comm_init with the same rank/world");
+    if (world > 1 && e->peers_attached) {
+        // Nobody stores into a peer's arena before that peer has ENTERED this run: in its stream order that is after
+        // everything it did with the previous run's results (downloads included), whose slots this run may reuse.
+        e->launches += launch_peer_barrier(e->peer_flags, e->my_flags, e->my_flags + 8, (int)rank, (int)world, ++e->epoch, e->stream);
+        CK(cudaGetLastError());
+    }
     for (uint32_t l = first_level; l < last_level; l++) {
         const uint32_t a = p->level_off[l], n_all = p->level_off[l + 1] - a, n_pbs = p->level_pbs[l];
         if (world == 1) {
@@ -516,11 +542,6 @@ int fhestr_program_run(fhestr_engine* e, fhestr_program* p, uint32_t first_level
             e->launches += launch_linear(p->d_jobs + a + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
             CK(cudaGetLastError());
         }
-    }
-    if (world > 1 && e->peers_attached) {
-        // nobody starts rewriting this program's slots (next run) before every rank has finished reading them
-        e->launches += launch_peer_barrier(e->peer_flags, e->my_flags, e->my_flags + 8, (int)rank, (int)world, ++e->epoch, e->stream);
-        CK(cudaGetLastError());
     }
     return FHESTR_OK;
 }
@@ -571,6 +592,10 @@ int fhestr_peer_attach(fhestr_engine* e, uint32_t rank, uint32_t world, const vo
         e->peer_arena[r] = static_cast<u64*>(pa);
         e->peer_flags[r] = static_cast<uint32_t*>(pf);
     }
+    // epochs restart at 0: stale flags of an earlier attachment must not satisfy a new barrier.  Every rank zeroes its
+    // own array here; the caller synchronises the ranks (any host barrier) between attach and the first run.
+    CK(cudaMemsetAsync(e->my_flags, 0, 16 * sizeof(uint32_t), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     e->rank = rank; e->world = world; e->peers_attached = true; e->epoch = 0;
     return FHESTR_OK;
 }

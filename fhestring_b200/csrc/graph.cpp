@@ -152,7 +152,19 @@ struct SignedScope {
 
 BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, const std::array<uint8_t, 16>& table) {
     std::vector<std::pair<BlockId, int>> ops = ops_in;
-    const uint32_t S = vset_of(ops, cst);
+    std::vector<Term> terms;
+    int c;
+    flatten(ops, cst, terms, c);
+    // value set of the input: the operands as given (lazy sums carry the range their recipe declared) AND the merged
+    // atoms (x - x vanishes, a block that occurs twice counts once with coefficient 2): both over-approximate the
+    // true set, so their intersection does too
+    auto atom_ops = [&]() {
+        std::vector<std::pair<BlockId, int>> a;
+        for (auto& t : terms) a.push_back({t.blk, t.coeff});
+        return a;
+    };
+    uint32_t S = vset_of(ops, cst) & vset_of(atom_ops(), c);
+    if (!S) S = vset_of(atom_ops(), c);
     if (S >> 16 & 1) fail("PBS input can reach the ambiguous value 16");
     if (!signed_ok && (S >> 16)) {
         std::string m = "PBS input overflows into the padding bit:";
@@ -167,12 +179,12 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     }
     if (popcount32(O) == 1) return trivial_block(__builtin_ctz(O));
 
-    std::vector<Term> terms;
-    int c;
-    flatten(ops, cst, terms, c);
-    // keep the input inside the variance the reference's own recipes use (graph.h): refresh the
-    // noisiest lazily-summed operand until it fits
-    for (int guard = 0; noise2_of(terms) > kNoise2Limit && guard < 8; guard++) {
+    // keep the input inside the variance the reference's own recipes use (graph.h).  First refresh the noisiest
+    // lazily-summed operand; when none qualifies, the excess sits in the COEFFICIENTS of the merged atoms (the same
+    // block summed m times -- identical windows over trivial chars, a string compared with itself, repeat_clear --
+    // counts m^2): such a term is replaced by ONE PBS that computes m * v from the block alone (input noise 1,
+    // output noise 1).  A refresh could not do that: the identity PBS of a block is one node however often it is asked for.
+    for (int guard = 0; noise2_of(terms) > kNoise2Limit && guard < 24; guard++) {
         int worst = -1;
         float worst_c = 0;
         for (size_t i = 0; i < ops.size(); i++) {
@@ -181,18 +193,39 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
             const float contrib = (float)ops[i].second * ops[i].second * n.noise2;
             if (contrib > worst_c) { worst_c = contrib; worst = (int)i; }
         }
-        if (worst < 0) {
+        if (worst >= 0) {
+            ops[worst].first = refresh(ops[worst].first);
+            flatten(ops, cst, terms, c);
+            continue;
+        }
+        int wt = -1;
+        worst_c = 0;
+        for (size_t i = 0; i < terms.size(); i++) {
+            const BlockNode& n = nodes[terms[i].blk];
+            const int m = std::abs(terms[i].coeff);
+            if (m < 2 || (n.vset >> 16) || n.noise2 > kNoise2Limit) continue;
+            bool fits = true;
+            for (int v = 0; v < 16; v++) if ((n.vset >> v & 1) && m * v > 15) fits = false;
+            const float contrib = (float)m * m * n.noise2;
+            if (fits && contrib > worst_c) { worst_c = contrib; wt = (int)i; }
+        }
+        if (wt < 0) {
             std::string m = "noise budget exceeded and nothing to refresh:";
-            for (auto& op : ops) {
-                const BlockNode& n = nodes[op.first];
-                m += " (" + std::to_string(op.second) + " x kind " + std::to_string((int)n.kind) + " noise2 " + std::to_string(n.noise2) + ")";
+            for (auto& t : terms) {
+                const BlockNode& n = nodes[t.blk];
+                m += " (" + std::to_string(t.coeff) + " x kind " + std::to_string((int)n.kind) + " noise2 " + std::to_string(n.noise2) + ")";
             }
             fail(m);
             break;
         }
-        ops[worst].first = refresh(ops[worst].first);
+        const int m = std::abs(terms[wt].coeff);
+        const BlockId scaled = pbs({{terms[wt].blk, 1}}, 0, table_of([m](int v) { return m * v; }));
+        ops = atom_ops();
+        ops[wt] = {scaled, terms[wt].coeff < 0 ? -1 : 1};
+        cst = c;
         flatten(ops, cst, terms, c);
     }
+    if (terms.empty()) return trivial_block(table[c & 15] * (c < 16 ? 1 : -1));
 
     const int lid = lut_id(table);
     std::string key;

@@ -39,10 +39,12 @@ class FheAsciiChar:
     """One encrypted u8 = 4 radix blocks.  Either a fresh host ciphertext (`ct`, from the client) or a value
     of a server key's graph (`sk`, `id`), or both once a fresh ciphertext has been handed to a server key."""
 
-    __slots__ = ("ct", "sk", "id")
+    __slots__ = ("ct", "sk", "id", "graph")
 
-    def __init__(self, ct=None, sk=None, id=None):
-        self.ct, self.sk, self.id = ct, sk, id
+    def __init__(self, ct=None, sk=None, id=None, graph=None):
+        # `graph` is the Graph instance `id` belongs to: MyServerKey.reset() starts a new graph, and an id of the
+        # old one must never be used in the new one (it would name an unrelated node)
+        self.ct, self.sk, self.id, self.graph = ct, sk, id, graph
 
     @staticmethod
     def encrypt_trivial(value: int, public_parameters, server_key: "MyServerKey") -> "FheAsciiChar":  # :17-25
@@ -118,7 +120,7 @@ class FheSplit:
 
 
 class MyClientKey:
-    """client_key.rs:9-106.  Host-side keygen / encrypt / decrypt through fhestr_client_* (seeded)."""
+    """client_key.rs:9-106.  Host-side keygen / encrypt / decrypt through fhestr_client_*."""
 
     def __init__(self, client: ClientKey, num_blocks: int = MAX_BLOCKS):
         assert num_blocks == MAX_BLOCKS
@@ -127,7 +129,8 @@ class MyClientKey:
         self._server_keys = None
 
     @staticmethod
-    def from_params(params: dict | None = None, num_blocks: int = MAX_BLOCKS, seed: int = 1) -> "MyClientKey":  # :30-35
+    def from_params(params: dict | None = None, num_blocks: int = MAX_BLOCKS, seed: int | None = None) -> "MyClientKey":  # :30-35
+        """seed=None: OS entropy (like the reference); an explicit seed is for reproducible tests only"""
         prm = dict(PARAM_MESSAGE_2_CARRY_2_KS_PBS)
         prm.update(params or {})
         return MyClientKey(ClientKey(seed=seed, **prm), num_blocks)
@@ -208,19 +211,27 @@ class MyServerKey:
         self.graph = Graph()
 
     # ---- plumbing between host ciphertexts, graph ids and the arena
+    def _mine(self, c: FheAsciiChar) -> bool:
+        return c.id is not None and c.sk is self and c.graph is self.graph
+
     def _adopt(self, c: FheAsciiChar) -> int:
-        if c.id is not None and c.sk is self:
+        if self._mine(c):
             return c.id
-        assert c.ct is not None, "char belongs to another server key"
+        if c.ct is None:
+            raise ValueError("this FheAsciiChar is a value of another server key, or of this one before reset(), "
+                             "and has no host ciphertext to re-upload")
         ids, slots = self.graph.input_chars(1)
         for b in range(4):
             self.engine.upload(int(slots[0, b]), c.ct[b])
-        c.sk, c.id = self, int(ids[0])
+        c.sk, c.id, c.graph = self, int(ids[0]), self.graph
         return c.id
 
     def _adopt_all(self, chars):
         chars = list(chars)
-        fresh = [c for c in chars if not (c.id is not None and c.sk is self)]
+        fresh = [c for c in chars if not self._mine(c)]
+        if any(c.ct is None for c in fresh):
+            raise ValueError("an FheAsciiChar is a value of another server key, or of this one before reset(), "
+                             "and has no host ciphertext to re-upload")
         if fresh:
             ids, slots = self.graph.input_chars(len(fresh))
             cts = np.stack([c.ct for c in fresh]).reshape(-1, self.engine.big)
@@ -229,11 +240,11 @@ class MyServerKey:
             assert (np.diff(flat.astype(np.int64)) == 1).all()
             self.engine.upload(int(flat[0]), cts)
             for c, i in zip(fresh, ids):
-                c.sk, c.id = self, int(i)
+                c.sk, c.id, c.graph = self, int(i), self.graph
         return np.array([c.id for c in chars], np.uint32)
 
     def _wrap(self, cid: int) -> FheAsciiChar:
-        return FheAsciiChar(sk=self, id=int(cid))
+        return FheAsciiChar(sk=self, id=int(cid), graph=self.graph)
 
     def _trivial(self, value: int) -> FheAsciiChar:
         return self._wrap(self.graph.trivial_chars([value & 255])[0])
@@ -244,6 +255,8 @@ class MyServerKey:
 
     def flush(self, outputs):
         """compile and run everything `outputs` depend on"""
+        if not all(self._mine(c) for c in outputs):
+            raise ValueError("flush() of a char that is not a value of this server key's current graph")
         ids = np.array([c.id for c in outputs], np.uint32)
         self.graph.mark_output(ids)
         self.last_info = self.graph.compile(self.world)

@@ -90,6 +90,10 @@ int fhestr_lut_download(fhestr_engine* e, int32_t lut_id, uint64_t* out_poly /* 
  * one must stay valid until the next synchronising call (fhestr_sync, fhestr_ct_download) */
 int fhestr_ct_upload(fhestr_engine* e, uint32_t first_block, uint32_t count, const uint64_t* host);
 int fhestr_ct_download(fhestr_engine* e, uint32_t first_block, uint32_t count, uint64_t* host);
+/* the same without the synchronisation: `pinned_host` must be page-locked and stay valid until the next synchronising
+ * call on the stream the copy was issued on (lets a caller overlap the copy-out of batch i with the PBS of batch i+1
+ * by switching streams with fhestr_set_stream and ordering them with its own events) */
+int fhestr_ct_download_async(fhestr_engine* e, uint32_t first_block, uint32_t count, uint64_t* pinned_host);
 /* create_trivial_radix (fheasciichar.rs:23): block b gets mask 0, body values[b] << delta_log */
 int fhestr_ct_trivial(fhestr_engine* e, uint32_t first_block, uint32_t count, const uint8_t* values);
 
@@ -205,7 +209,10 @@ int fhestr_comm_destroy(fhestr_engine* e);
  * as cudaIpc handles (64 bytes each), the host exchanges them, fhestr_peer_attach maps the peers' memory; from
  * then on the sample-extract epilogue of the blind rotation stores each result block into ALL arenas over NVLink
  * and a flag barrier over peer memory closes the level.  arena_handles / flags_handles: [world][64] bytes by rank.
- * fhestr_peer_status reports whether a barrier ever timed out (a peer died). */
+ * A barrier that times out (a peer died) sets a status word: every synchronising call (fhestr_sync,
+ * fhestr_ct_download, fhestr_graph_execute) then fails with FHESTR_E_STATE instead of handing out incomplete
+ * results; fhestr_peer_status reads the word.  A run starts with one such barrier, so no rank stores into a peer's
+ * arena before that peer has finished with the previous run's results. */
 int fhestr_peer_export(fhestr_engine* e, void* arena_handle_64, void* flags_handle_64);
 int fhestr_peer_attach(fhestr_engine* e, uint32_t rank, uint32_t world, const void* arena_handles, const void* flags_handles);
 int fhestr_peer_detach(fhestr_engine* e);
@@ -243,7 +250,9 @@ int fhestr_get_timing(fhestr_engine* e, double* keyswitch_ms, double* blind_rota
 
 /* ---- client side (replaces MyClientKey, /root/reference/src/client_key.rs:9-106): host-only ------- */
 /* Key generation, block/string encryption and decryption.  Runs on the CPU like the reference's
- * client; it is not on the PBS path.  Deterministic for a given seed. */
+ * client; it is not on the PBS path.  All randomness (secret keys, masks, noise) is ChaCha20 output under a 256-bit
+ * key: seed == 0 takes that key from the operating system (getrandom) -- the production setting, as tfhe-rs seeds
+ * gen_keys_radix; seed != 0 derives it from the seed and is for TESTS AND BENCHMARKS ONLY (reproducible keys). */
 typedef struct fhestr_client fhestr_client;
 int fhestr_client_create(const fhestr_params* params, double lwe_std, double glwe_std, uint64_t seed,
                          fhestr_client** out);

@@ -114,6 +114,18 @@ static inline void decompose(u64 x, int base_log, int level, i64 *digits) {
 
 void orc_decompose(u64 x, int base_log, int level, i64 *digits) { decompose(x, base_log, level, digits); }
 
+/* the same for level == 1 over a whole polynomial: digit = d - B [d > B/2], d = round(x / 2^(64-base_log)) mod B
+ * (identical values to decompose(x, base_log, 1, .): tests/test_oracle_tfhe.py checks it) */
+CLONES static void decompose1_poly(const u64 *restrict x, int base_log, int n, i64 *restrict out) {
+    const int r = 64 - base_log;
+    const u64 mask = (((u64)1) << base_log) - 1, half = ((u64)1) << (base_log - 1);
+    for (int j = 0; j < n; j++) {
+        const u64 d = (((x[j] >> (r - 1)) + 1) >> 1) & mask;
+        out[j] = (i64)d - (i64)((d > half) ? (mask + 1) : 0);
+    }
+}
+void orc_decompose1_poly(const u64 *x, int base_log, int n, i64 *out) { decompose1_poly(x, base_log, n, out); }
+
 /* ------------------------------------------------------------------ A.6 modulus switch to 2N */
 static inline u32 modswitch(u64 x, int log2_2N) {
     u64 t = x >> (64 - log2_2N - 1);
@@ -218,7 +230,10 @@ void orc_lwe_phase_batch(const u8 *key, int dim, const u64 *cts, int count, u64 
 }
 
 /* ------------------------------------------------------------------ A.5 keyswitch */
-CLONES void orc_keyswitch(const orc_params *p, const u64 *ksk, const u64 *in, u64 *out) {
+CLONES CLONES static void sub_scaled_row(u64 *restrict out, const u64 *restrict row, u64 d, int len) {
+    for (int c = 0; c < len; c++) out[c] -= d * row[c];
+}
+void orc_keyswitch(const orc_params *p, const u64 *ksk, const u64 *in, u64 *out) {
     const int n = p->n, Nb = p->N * p->k, L = p->ks_level;
     i64 digits[64];
     for (int c = 0; c < n; c++) out[c] = 0;
@@ -228,8 +243,7 @@ CLONES void orc_keyswitch(const orc_params *p, const u64 *ksk, const u64 *in, u6
         for (int lvl = 1; lvl <= L; lvl++) {
             const u64 d = (u64)digits[lvl - 1];
             if (!d) continue;
-            const u64 *row = ksk + ((size_t)i * L + (lvl - 1)) * (n + 1);
-            for (int c = 0; c <= n; c++) out[c] -= d * row[c];
+            sub_scaled_row(out, ksk + ((size_t)i * L + (lvl - 1)) * (n + 1), d, n + 1);
         }
     }
 }
@@ -254,7 +268,7 @@ void orc_lut_poly(int N, const u8 *table, int delta_log, u64 *out) {
 
 /* ------------------------------------------------------------------ negacyclic helpers */
 /* out = in * X^e, e in [0, 2N) */
-static void monomial_mul(u64 *out, const u64 *in, int e, int N) {
+CLONES static void monomial_mul(u64 *restrict out, const u64 *restrict in, int e, int N) {
     int neg = 0;
     if (e >= N) { e -= N; neg = 1; }
     for (int j = 0; j < N - e; j++) out[j + e] = neg ? (u64)0 - in[j] : in[j];
@@ -334,100 +348,316 @@ void orc_pbs_exact_batch(const orc_params *p, const u64 *bsk, const u64 *ksk, co
 
 /* ------------------------------------------------------------------ f64 negacyclic FFT route */
 /* X_k = P(y_k), y_k = exp(i*pi*(1-4k)/N), k < N/2, via fold (p_j + i p_{j+N/2}), twist exp(i*pi*j/N),
- * then an N/2-point forward DFT (DIF, output bit-reversed).  The inverse is a DIT taking the
- * bit-reversed order back to natural, so no permutation is ever materialised. */
+ * then an M = N/2-point forward DFT done FOUR-STEP: the M points are an R x C matrix (row-major, n = C r + c);
+ * pass 1 is a length-R DIF over the ROWS (every butterfly works on two whole rows, i.e. on C contiguous doubles:
+ * unit-stride loops that gcc vectorises for AVX2 / AVX-512 through the target clones, scalar twiddles), then the
+ * inter-pass twiddle, a transpose, and pass 2, a length-C DIF over the rows of the transposed matrix.  The spectrum
+ * comes out in a fixed private order (bit-reversed in both passes); the Fourier key is produced by the same
+ * function and the inverse mirrors the forward, so no permutation is ever materialised.  This is the same
+ * decomposition tfhe-rs' concrete-fft uses for this size class (split re/im, radix passes over SIMD lanes); the
+ * first version of this file was a plain radix-2 loop with strided twiddles, three times slower. */
 typedef struct {
-    int N, M;
-    double *tw_re, *tw_im;       /* exp(-2 pi i j / M), j < M/2 */
+    int N, M, R, C;
     double *twist_re, *twist_im; /* exp(i pi j / N), j < M */
+    double *w1_re, *w1_im;       /* exp(-2 pi i j / R), j < R/2 */
+    double *w2_re, *w2_im;       /* exp(-2 pi i j / C), j < C/2 */
+    double *tm_re, *tm_im;       /* [R][C]: exp(-2 pi i c k1(r) / M), k1(r) = the frequency pass 1 leaves in row r */
+    double *w32_re, *w32_im;     /* 32 x 32 case: exp(-2 pi i b c / 32), [b*4 + c] */
 } fft_plan;
+
+static int bitrev(int x, int bits) { int r = 0; for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i); return r; }
 
 fft_plan *orc_fft_plan_new(int N) {
     fft_plan *pl = (fft_plan *)malloc(sizeof(fft_plan));
-    const int M = N / 2;
-    pl->N = N; pl->M = M;
-    pl->tw_re = (double *)malloc(sizeof(double) * M / 2);
-    pl->tw_im = (double *)malloc(sizeof(double) * M / 2);
+    const int M = N / 2, lm = ilog2(M);
+    const int R = 1 << ((lm + 1) / 2), C = M / R;
+    const long double PI = 3.14159265358979323846264338327950288L;
+    pl->N = N; pl->M = M; pl->R = R; pl->C = C;
     pl->twist_re = (double *)malloc(sizeof(double) * M);
     pl->twist_im = (double *)malloc(sizeof(double) * M);
-    for (int j = 0; j < M / 2; j++) {
-        long double a = -2.0L * 3.14159265358979323846264338327950288L * j / M;
-        pl->tw_re[j] = (double)cosl(a); pl->tw_im[j] = (double)sinl(a);
-    }
+    pl->w1_re = (double *)malloc(sizeof(double) * (R / 2 + 1));
+    pl->w1_im = (double *)malloc(sizeof(double) * (R / 2 + 1));
+    pl->w2_re = (double *)malloc(sizeof(double) * (C / 2 + 1));
+    pl->w2_im = (double *)malloc(sizeof(double) * (C / 2 + 1));
+    pl->tm_re = (double *)malloc(sizeof(double) * M);
+    pl->tm_im = (double *)malloc(sizeof(double) * M);
     for (int j = 0; j < M; j++) {
-        long double a = 3.14159265358979323846264338327950288L * j / N;
+        long double a = PI * j / N;
         pl->twist_re[j] = (double)cosl(a); pl->twist_im[j] = (double)sinl(a);
+    }
+    for (int j = 0; j < R / 2; j++) { long double a = -2.0L * PI * j / R; pl->w1_re[j] = (double)cosl(a); pl->w1_im[j] = (double)sinl(a); }
+    for (int j = 0; j < C / 2; j++) { long double a = -2.0L * PI * j / C; pl->w2_re[j] = (double)cosl(a); pl->w2_im[j] = (double)sinl(a); }
+    pl->w32_re = (double *)malloc(sizeof(double) * 32);
+    pl->w32_im = (double *)malloc(sizeof(double) * 32);
+    for (int b = 0; b < 8; b++)
+        for (int c = 0; c < 4; c++) {
+            long double a = -2.0L * PI * (b * c) / 32;
+            pl->w32_re[b * 4 + c] = (double)cosl(a); pl->w32_im[b * 4 + c] = (double)sinl(a);
+        }
+    for (int r = 0; r < R; r++) {
+        /* generic: bit-reversed rows; 32 x 32: row 8c + d holds frequency c + 4d (rows32_fwd) */
+        const int k1 = (R == 32 && C == 32) ? ((r >> 3) + 4 * (r & 7)) : bitrev(r, ilog2(R));
+        for (int c = 0; c < C; c++) {
+            long double a = -2.0L * PI * (long double)((long)c * k1 % M) / M;
+            pl->tm_re[r * C + c] = (double)cosl(a); pl->tm_im[r * C + c] = (double)sinl(a);
+        }
     }
     return pl;
 }
 void orc_fft_plan_free(fft_plan *pl) {
-    free(pl->tw_re); free(pl->tw_im); free(pl->twist_re); free(pl->twist_im); free(pl);
+    free(pl->twist_re); free(pl->twist_im); free(pl->w1_re); free(pl->w1_im); free(pl->w2_re); free(pl->w2_im);
+    free(pl->tm_re); free(pl->tm_im); free(pl->w32_re); free(pl->w32_im); free(pl);
 }
 
-/* in-place DIF forward, natural in -> bit-reversed out (split re/im arrays) */
-CLONES static void fft_dif(const fft_plan *pl, double *re, double *im) {
-    const int M = pl->M;
-    for (int half = M / 2, stride = 1; half >= 1; half >>= 1, stride <<= 1) {
-        for (int base = 0; base < M; base += 2 * half) {
-            double *ar = re + base, *ai = im + base, *br = re + base + half, *bi = im + base + half;
+/* length-R DIF over the rows of an R x C matrix (split re/im), natural rows in -> bit-reversed rows out */
+CLONES static void rows_dif(double *restrict re, double *restrict im, int R, int C, const double *wr, const double *wi) {
+    for (int half = R / 2, stride = 1; half >= 1; half >>= 1, stride <<= 1)
+        for (int base = 0; base < R; base += 2 * half)
             for (int j = 0; j < half; j++) {
-                const double wr = pl->tw_re[j * stride], wi = pl->tw_im[j * stride];
-                const double xr = ar[j] - br[j], xi = ai[j] - bi[j];
-                ar[j] += br[j]; ai[j] += bi[j];
-                br[j] = xr * wr - xi * wi; bi[j] = xr * wi + xi * wr;
+                const double cr = wr[j * stride], ci = wi[j * stride];
+                double *restrict ar = re + (size_t)(base + j) * C, *restrict ai = im + (size_t)(base + j) * C;
+                double *restrict br = re + (size_t)(base + j + half) * C, *restrict bi = im + (size_t)(base + j + half) * C;
+                for (int c = 0; c < C; c++) {
+                    const double xr = ar[c] - br[c], xi = ai[c] - bi[c];
+                    ar[c] += br[c]; ai[c] += bi[c];
+                    br[c] = xr * cr - xi * ci; bi[c] = xr * ci + xi * cr;
+                }
+            }
+}
+/* the mirror: DIT with conjugate twiddles, bit-reversed rows in -> natural rows out, unscaled */
+CLONES static void rows_dit_inv(double *restrict re, double *restrict im, int R, int C, const double *wr, const double *wi) {
+    for (int half = 1, stride = R / 2; half < R; half <<= 1, stride >>= 1)
+        for (int base = 0; base < R; base += 2 * half)
+            for (int j = 0; j < half; j++) {
+                const double cr = wr[j * stride], ci = -wi[j * stride];
+                double *restrict ar = re + (size_t)(base + j) * C, *restrict ai = im + (size_t)(base + j) * C;
+                double *restrict br = re + (size_t)(base + j + half) * C, *restrict bi = im + (size_t)(base + j + half) * C;
+                for (int c = 0; c < C; c++) {
+                    const double tr = br[c] * cr - bi[c] * ci, ti = br[c] * ci + bi[c] * cr;
+                    br[c] = ar[c] - tr; bi[c] = ai[c] - ti;
+                    ar[c] += tr; ai[c] += ti;
+                }
+            }
+}
+CLONES static void transpose(const double *restrict in, double *restrict out, int R, int C) { /* in R x C -> out C x R */
+    for (int r0 = 0; r0 < R; r0 += 8)
+        for (int c0 = 0; c0 < C; c0 += 8)
+            for (int r = r0; r < r0 + 8 && r < R; r++)
+                for (int c = c0; c < c0 + 8 && c < C; c++) out[(size_t)c * R + r] = in[(size_t)r * C + c];
+}
+/* ---- the 32 x 32 case (N = 2048, the only size the parameter set uses) with every row pass done in registers:
+ * a length-32 DFT over rows is a 4-point DFT over a (rows 8a + b), the twiddle W32^(bc), and an 8-point DFT over b
+ * (n = 8a + b, k = c + 4d: row 8c + d ends up holding frequency c + 4d) -- two passes over the matrix instead of five
+ * radix-2 ones, on vectors of 4 columns (GCC vector extensions: SSE2 pairs, AVX2 or AVX-512VL by clone). */
+typedef double v4d __attribute__((vector_size(32), aligned(8)));
+#define LD(p) (*(const v4d *)(p))
+#define ST(p, v) (*(v4d *)(p) = (v))
+#define SQH 0.70710678118654752440
+
+/* in-register 8-point DFT, sign = -1 forward / +1 inverse (exp(sign 2 pi i bd / 8)), natural order in and out */
+#define DFT8(xr, xi, SGN)                                                                              \
+    do {                                                                                               \
+        v4d ar[8], ai[8];                                                                              \
+        for (int q = 0; q < 4; q++) {                                                                  \
+            ar[q] = xr[q] + xr[q + 4]; ai[q] = xi[q] + xi[q + 4];                                      \
+            ar[q + 4] = xr[q] - xr[q + 4]; ai[q + 4] = xi[q] - xi[q + 4];                              \
+        }                                                                                              \
+        /* odd half: times W8^q (q = 0..3) */                                                          \
+        {                                                                                              \
+            v4d tr, ti;                                                                                \
+            tr = ar[5]; ti = ai[5];                                                                    \
+            if (SGN < 0) { ar[5] = (tr + ti) * SQH; ai[5] = (ti - tr) * SQH; }                         \
+            else { ar[5] = (tr - ti) * SQH; ai[5] = (ti + tr) * SQH; }                                 \
+            tr = ar[6]; ti = ai[6];                                                                    \
+            if (SGN < 0) { ar[6] = ti; ai[6] = -tr; } else { ar[6] = -ti; ai[6] = tr; }                \
+            tr = ar[7]; ti = ai[7];                                                                    \
+            if (SGN < 0) { ar[7] = (ti - tr) * SQH; ai[7] = -(tr + ti) * SQH; }                        \
+            else { ar[7] = -(tr + ti) * SQH; ai[7] = (tr - ti) * SQH; }                                \
+        }                                                                                              \
+        /* two 4-point DFTs: even outputs from ar[0..3], odd outputs from ar[4..7] */                  \
+        for (int h = 0; h < 2; h++) {                                                                  \
+            v4d *r = ar + 4 * h, *i_ = ai + 4 * h;                                                     \
+            const v4d s0r = r[0] + r[2], s0i = i_[0] + i_[2], d0r = r[0] - r[2], d0i = i_[0] - i_[2];  \
+            const v4d s1r = r[1] + r[3], s1i = i_[1] + i_[3], d1r = r[1] - r[3], d1i = i_[1] - i_[3];  \
+            xr[h] = s0r + s1r; xi[h] = s0i + s1i;                                                      \
+            xr[h + 4] = s0r - s1r; xi[h + 4] = s0i - s1i;                                              \
+            if (SGN < 0) { xr[h + 2] = d0r + d1i; xi[h + 2] = d0i - d1r; xr[h + 6] = d0r - d1i; xi[h + 6] = d0i + d1r; } \
+            else { xr[h + 2] = d0r - d1i; xi[h + 2] = d0i + d1r; xr[h + 6] = d0r + d1i; xi[h + 6] = d0i - d1r; }         \
+        }                                                                                              \
+    } while (0)
+
+/* w32[b*4 + c] = exp(-2 pi i b c / 32) */
+CLONES static void rows32_fwd(double *restrict re, double *restrict im, const double *w32r, const double *w32i) {
+    for (int b = 0; b < 8; b++)
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            v4d xr[4], xi[4];
+            for (int a = 0; a < 4; a++) { xr[a] = LD(re + (8 * a + b) * 32 + c0); xi[a] = LD(im + (8 * a + b) * 32 + c0); }
+            const v4d s0r = xr[0] + xr[2], s0i = xi[0] + xi[2], d0r = xr[0] - xr[2], d0i = xi[0] - xi[2];
+            const v4d s1r = xr[1] + xr[3], s1i = xi[1] + xi[3], d1r = xr[1] - xr[3], d1i = xi[1] - xi[3];
+            v4d yr[4], yi[4];
+            yr[0] = s0r + s1r; yi[0] = s0i + s1i;
+            yr[2] = s0r - s1r; yi[2] = s0i - s1i;
+            yr[1] = d0r + d1i; yi[1] = d0i - d1r;      /* -i */
+            yr[3] = d0r - d1i; yi[3] = d0i + d1r;
+            ST(re + b * 32 + c0, yr[0]); ST(im + b * 32 + c0, yi[0]);
+            for (int c = 1; c < 4; c++) {
+                const double wr = w32r[b * 4 + c], wi = w32i[b * 4 + c];
+                ST(re + (8 * c + b) * 32 + c0, yr[c] * wr - yi[c] * wi);
+                ST(im + (8 * c + b) * 32 + c0, yr[c] * wi + yi[c] * wr);
             }
         }
-    }
+    for (int c = 0; c < 4; c++)
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            v4d xr[8], xi[8];
+            for (int q = 0; q < 8; q++) { xr[q] = LD(re + (8 * c + q) * 32 + c0); xi[q] = LD(im + (8 * c + q) * 32 + c0); }
+            DFT8(xr, xi, -1);
+            for (int q = 0; q < 8; q++) { ST(re + (8 * c + q) * 32 + c0, xr[q]); ST(im + (8 * c + q) * 32 + c0, xi[q]); }
+        }
 }
-/* in-place DIT inverse (conjugate twiddles), bit-reversed in -> natural out, unscaled */
-CLONES static void fft_dit_inv(const fft_plan *pl, double *re, double *im) {
-    const int M = pl->M;
-    for (int half = 1, stride = M / 2; half < M; half <<= 1, stride >>= 1) {
-        for (int base = 0; base < M; base += 2 * half) {
-            double *ar = re + base, *ai = im + base, *br = re + base + half, *bi = im + base + half;
-            for (int j = 0; j < half; j++) {
-                const double wr = pl->tw_re[j * stride], wi = -pl->tw_im[j * stride];
-                const double tr = br[j] * wr - bi[j] * wi, ti = br[j] * wi + bi[j] * wr;
-                br[j] = ar[j] - tr; bi[j] = ai[j] - ti;
-                ar[j] += tr; ai[j] += ti;
+CLONES static void rows32_inv(double *restrict re, double *restrict im, const double *w32r, const double *w32i) {
+    for (int c = 0; c < 4; c++)
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            v4d xr[8], xi[8];
+            for (int q = 0; q < 8; q++) { xr[q] = LD(re + (8 * c + q) * 32 + c0); xi[q] = LD(im + (8 * c + q) * 32 + c0); }
+            DFT8(xr, xi, +1);
+            for (int q = 0; q < 8; q++) { ST(re + (8 * c + q) * 32 + c0, xr[q]); ST(im + (8 * c + q) * 32 + c0, xi[q]); }
+        }
+    for (int b = 0; b < 8; b++)
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            v4d xr[4], xi[4];
+            xr[0] = LD(re + b * 32 + c0); xi[0] = LD(im + b * 32 + c0);
+            for (int c = 1; c < 4; c++) {
+                const double wr = w32r[b * 4 + c], wi = -w32i[b * 4 + c];
+                const v4d tr = LD(re + (8 * c + b) * 32 + c0), ti = LD(im + (8 * c + b) * 32 + c0);
+                xr[c] = tr * wr - ti * wi; xi[c] = tr * wi + ti * wr;
+            }
+            const v4d s0r = xr[0] + xr[2], s0i = xi[0] + xi[2], d0r = xr[0] - xr[2], d0i = xi[0] - xi[2];
+            const v4d s1r = xr[1] + xr[3], s1i = xi[1] + xi[3], d1r = xr[1] - xr[3], d1i = xi[1] - xi[3];
+            ST(re + b * 32 + c0, s0r + s1r); ST(im + b * 32 + c0, s0i + s1i);
+            ST(re + (16 + b) * 32 + c0, s0r - s1r); ST(im + (16 + b) * 32 + c0, s0i - s1i);
+            ST(re + (8 + b) * 32 + c0, d0r - d1i); ST(im + (8 + b) * 32 + c0, d0i + d1r);     /* +i */
+            ST(re + (24 + b) * 32 + c0, d0r + d1i); ST(im + (24 + b) * 32 + c0, d0i - d1r);
+        }
+}
+/* out[c][r] = in[r][c] * (tw[r][c] or its conjugate), 32 x 32, 4 x 4 blocks transposed in registers */
+CLONES static void transpose32_tw(const double *restrict ir, const double *restrict ii, double *restrict or_, double *restrict oi,
+                                  const double *restrict twr, const double *restrict twi, int conj_after) {
+    for (int r0 = 0; r0 < 32; r0 += 4)
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            v4d ar[4], ai[4];
+            for (int q = 0; q < 4; q++) {
+                v4d xr = LD(ir + (r0 + q) * 32 + c0), xi = LD(ii + (r0 + q) * 32 + c0);
+                if (!conj_after) {   /* forward: twiddle indexed like the INPUT (r, c) */
+                    const v4d wr = LD(twr + (r0 + q) * 32 + c0), wi = LD(twi + (r0 + q) * 32 + c0);
+                    ar[q] = xr * wr - xi * wi; ai[q] = xr * wi + xi * wr;
+                } else { ar[q] = xr; ai[q] = xi; }
+            }
+            v4d br[4], bi[4];
+#define T4(a, b)                                                                             \
+            do {                                                                             \
+                const v4d t0 = __builtin_shuffle(a[0], a[1], (__typeof__((long long __attribute__((vector_size(32)))){0})){0, 4, 2, 6}); \
+                const v4d t1 = __builtin_shuffle(a[0], a[1], (__typeof__((long long __attribute__((vector_size(32)))){0})){1, 5, 3, 7}); \
+                const v4d t2 = __builtin_shuffle(a[2], a[3], (__typeof__((long long __attribute__((vector_size(32)))){0})){0, 4, 2, 6}); \
+                const v4d t3 = __builtin_shuffle(a[2], a[3], (__typeof__((long long __attribute__((vector_size(32)))){0})){1, 5, 3, 7}); \
+                b[0] = __builtin_shuffle(t0, t2, (__typeof__((long long __attribute__((vector_size(32)))){0})){0, 1, 4, 5}); \
+                b[1] = __builtin_shuffle(t1, t3, (__typeof__((long long __attribute__((vector_size(32)))){0})){0, 1, 4, 5}); \
+                b[2] = __builtin_shuffle(t0, t2, (__typeof__((long long __attribute__((vector_size(32)))){0})){2, 3, 6, 7}); \
+                b[3] = __builtin_shuffle(t1, t3, (__typeof__((long long __attribute__((vector_size(32)))){0})){2, 3, 6, 7}); \
+            } while (0)
+            T4(ar, br); T4(ai, bi);
+            for (int q = 0; q < 4; q++) {
+                if (conj_after) {    /* inverse: conj twiddle indexed like the OUTPUT (row c0+q, col r0..) */
+                    const v4d wr = LD(twr + (c0 + q) * 32 + r0), wi = LD(twi + (c0 + q) * 32 + r0);
+                    ST(or_ + (c0 + q) * 32 + r0, br[q] * wr + bi[q] * wi);
+                    ST(oi + (c0 + q) * 32 + r0, bi[q] * wr - br[q] * wi);
+                } else { ST(or_ + (c0 + q) * 32 + r0, br[q]); ST(oi + (c0 + q) * 32 + r0, bi[q]); }
             }
         }
-    }
 }
-/* forward transform of a signed-integer polynomial */
-CLONES static void fwd_i64(const fft_plan *pl, const i64 *p, double *re, double *im) {
+
+/* forward M-point DFT of (re, im) (already twisted), result in (re, im) in the plan's private order; t: 2M scratch */
+static void fft_fwd(const fft_plan *pl, double *restrict re, double *restrict im, double *restrict t) {
+    const int M = pl->M, R = pl->R, C = pl->C;
+    if (R == 32 && C == 32) {
+        rows32_fwd(re, im, pl->w32_re, pl->w32_im);
+        transpose32_tw(re, im, t, t + M, pl->tm_re, pl->tm_im, 0);
+        rows32_fwd(t, t + M, pl->w32_re, pl->w32_im);
+        memcpy(re, t, sizeof(double) * M); memcpy(im, t + M, sizeof(double) * M);
+        return;
+    }
+    rows_dif(re, im, R, C, pl->w1_re, pl->w1_im);
+    for (int j = 0; j < M; j++) {
+        const double a = re[j], b = im[j];
+        re[j] = a * pl->tm_re[j] - b * pl->tm_im[j];
+        im[j] = a * pl->tm_im[j] + b * pl->tm_re[j];
+    }
+    transpose(re, t, R, C); transpose(im, t + M, R, C);
+    rows_dif(t, t + M, C, R, pl->w2_re, pl->w2_im);
+    memcpy(re, t, sizeof(double) * M); memcpy(im, t + M, sizeof(double) * M);
+}
+/* inverse of fft_fwd, unscaled (x M) */
+static void fft_inv(const fft_plan *pl, double *restrict re, double *restrict im, double *restrict t) {
+    const int M = pl->M, R = pl->R, C = pl->C;
+    if (R == 32 && C == 32) {
+        rows32_inv(re, im, pl->w32_re, pl->w32_im);
+        transpose32_tw(re, im, t, t + M, pl->tm_re, pl->tm_im, 1);
+        rows32_inv(t, t + M, pl->w32_re, pl->w32_im);
+        memcpy(re, t, sizeof(double) * M); memcpy(im, t + M, sizeof(double) * M);
+        return;
+    }
+    rows_dit_inv(re, im, C, R, pl->w2_re, pl->w2_im);
+    transpose(re, t, C, R); transpose(im, t + M, C, R);
+    for (int j = 0; j < M; j++) {
+        const double a = t[j], b = t[M + j];
+        re[j] = a * pl->tm_re[j] + b * pl->tm_im[j];
+        im[j] = b * pl->tm_re[j] - a * pl->tm_im[j];
+    }
+    rows_dit_inv(re, im, R, C, pl->w1_re, pl->w1_im);
+}
+/* forward transform of a signed-integer polynomial; t: 2M doubles of scratch */
+CLONES static void twist_i64(const fft_plan *pl, const i64 *restrict p, double *restrict re, double *restrict im) {
     const int M = pl->M;
+    const double *restrict tr = pl->twist_re, *restrict ti = pl->twist_im;
     for (int j = 0; j < M; j++) {
         const double a = (double)p[j], b = (double)p[j + M];
-        re[j] = a * pl->twist_re[j] - b * pl->twist_im[j];
-        im[j] = a * pl->twist_im[j] + b * pl->twist_re[j];
+        re[j] = a * tr[j] - b * ti[j];
+        im[j] = a * ti[j] + b * tr[j];
     }
-    fft_dif(pl, re, im);
+}
+static void fwd_i64(const fft_plan *pl, const i64 *p, double *restrict re, double *restrict im, double *restrict t) {
+    twist_i64(pl, p, re, im);
+    fft_fwd(pl, re, im, t);
 }
 /* Fourier image of a torus polynomial read as signed i64 scaled by 2^-64 (the BSK conversion) */
 void orc_fft_forward_torus(const fft_plan *pl, const u64 *p, double *re, double *im) {
     const int M = pl->M;
     const double sc = 1.0 / 18446744073709551616.0;
+    double *t = (double *)malloc(sizeof(double) * 2 * M);
     for (int j = 0; j < M; j++) {
         const double a = (double)(i64)p[j] * sc, b = (double)(i64)p[j + M] * sc;
         re[j] = a * pl->twist_re[j] - b * pl->twist_im[j];
         im[j] = a * pl->twist_im[j] + b * pl->twist_re[j];
     }
-    fft_dif(pl, re, im);
+    fft_fwd(pl, re, im, t);
+    free(t);
 }
 /* inverse transform, result added to a torus polynomial: acc += round(frac(x) * 2^64) */
-CLONES static void inv_add_torus(const fft_plan *pl, double *re, double *im, u64 *acc) {
+CLONES static void untwist_add_torus(const fft_plan *pl, const double *restrict re, const double *restrict im, u64 *restrict acc) {
     const int M = pl->M;
     const double inv = 1.0 / M;
-    fft_dit_inv(pl, re, im);
+    const double *restrict tr = pl->twist_re, *restrict ti = pl->twist_im;
     for (int j = 0; j < M; j++) {
         /* untwist by exp(-i pi j / N) */
-        const double cr = pl->twist_re[j], ci = -pl->twist_im[j];
+        const double cr = tr[j], ci = -ti[j];
         double a = (re[j] * cr - im[j] * ci) * inv, b = (re[j] * ci + im[j] * cr) * inv;
         a -= rint(a); b -= rint(b);
         acc[j] += (u64)(i64)llrint(a * 18446744073709551616.0);
         acc[j + M] += (u64)(i64)llrint(b * 18446744073709551616.0);
     }
+}
+static void inv_add_torus(const fft_plan *pl, double *restrict re, double *restrict im, u64 *restrict acc, double *restrict t) {
+    fft_inv(pl, re, im, t);
+    untwist_add_torus(pl, re, im, acc);
 }
 
 /* Fourier BSK: [n][level][2 rows][2 cols] x (re[M], im[M]) doubles */
@@ -441,35 +671,42 @@ void orc_fourier_bsk(const orc_params *p, const u64 *bsk, double *fbsk) {
     orc_fft_plan_free(pl);
 }
 
-/* FFT external product on one GGSW: acc[2][N] += ggsw_f (x) glwe[2][N].  scratch: 6*M doubles + N i64 */
+CLONES static void cmul_acc2(const double *restrict dr, const double *restrict di, const double *restrict g0, const double *restrict g1,
+                             double *restrict o0r, double *restrict o0i, double *restrict o1r, double *restrict o1i, int M) {
+    for (int j = 0; j < M; j++) {
+        o0r[j] += dr[j] * g0[j] - di[j] * g0[j + M];
+        o0i[j] += dr[j] * g0[j + M] + di[j] * g0[j];
+        o1r[j] += dr[j] * g1[j] - di[j] * g1[j + M];
+        o1i[j] += dr[j] * g1[j + M] + di[j] * g1[j];
+    }
+}
+/* FFT external product on one GGSW: acc[2][N] += ggsw_f (x) glwe[2][N].  scratch: 8*M doubles + N i64 */
 static void external_product_fft(const orc_params *p, const fft_plan *pl, const double *gf, const u64 *glwe,
                                  u64 *acc, double *scratch, i64 *dig) {
     const int N = p->N, M = N / 2, L = p->pbs_level;
     double *dre = scratch, *dim_ = scratch + M;
     double *o0r = scratch + 2 * M, *o0i = scratch + 3 * M, *o1r = scratch + 4 * M, *o1i = scratch + 5 * M;
+    double *tsc = scratch + 6 * M;
     i64 tmp[64];
     memset(o0r, 0, sizeof(double) * 4 * M);
     for (int r = 0; r < 2; r++)
         for (int l = 0; l < L; l++) {
-            for (int j = 0; j < N; j++) {
-                decompose(glwe[r * N + j], p->pbs_base_log, L, tmp);
-                dig[j] = tmp[l];
-            }
-            fwd_i64(pl, dig, dre, dim_);
+            if (L == 1) decompose1_poly(glwe + r * N, p->pbs_base_log, N, dig);
+            else
+                for (int j = 0; j < N; j++) {
+                    decompose(glwe[r * N + j], p->pbs_base_log, L, tmp);
+                    dig[j] = tmp[l];
+                }
+            fwd_i64(pl, dig, dre, dim_, tsc);
             const double *g0 = gf + (((size_t)l * 2 + r) * 2 + 0) * N, *g1 = g0 + N;
-            for (int j = 0; j < M; j++) {
-                o0r[j] += dre[j] * g0[j] - dim_[j] * g0[j + M];
-                o0i[j] += dre[j] * g0[j + M] + dim_[j] * g0[j];
-                o1r[j] += dre[j] * g1[j] - dim_[j] * g1[j + M];
-                o1i[j] += dre[j] * g1[j + M] + dim_[j] * g1[j];
-            }
+            cmul_acc2(dre, dim_, g0, g1, o0r, o0i, o1r, o1i, M);
         }
-    inv_add_torus(pl, o0r, o0i, acc);
-    inv_add_torus(pl, o1r, o1i, acc + N);
+    inv_add_torus(pl, o0r, o0i, acc, tsc);
+    inv_add_torus(pl, o1r, o1i, acc + N, tsc);
 }
 void orc_external_product_fft(const orc_params *p, const double *ggsw_f, const u64 *glwe, u64 *acc) {
     fft_plan *pl = orc_fft_plan_new(p->N);
-    double *scratch = (double *)malloc(sizeof(double) * 3 * p->N);
+    double *scratch = (double *)malloc(sizeof(double) * 4 * p->N);
     i64 *dig = (i64 *)malloc(sizeof(i64) * p->N);
     external_product_fft(p, pl, ggsw_f, glwe, acc, scratch, dig);
     free(scratch); free(dig); orc_fft_plan_free(pl);
@@ -479,7 +716,7 @@ void orc_blind_rotate_fft(const orc_params *p, const fft_plan *pl, const double 
                           const u64 *lut, u64 *acc) {
     const int n = p->n, N = p->N, lg = ilog2(2 * N);
     u64 *rot = (u64 *)malloc(sizeof(u64) * 2 * N);
-    double *scratch = (double *)malloc(sizeof(double) * 3 * N);
+    double *scratch = (double *)malloc(sizeof(double) * 4 * N);
     i64 *dig = (i64 *)malloc(sizeof(i64) * N);
     u32 bt = modswitch(ks[n], lg) % (2 * N);
     memset(acc, 0, sizeof(u64) * N);
@@ -497,29 +734,84 @@ void orc_blind_rotate_fft(const orc_params *p, const fft_plan *pl, const double 
     free(rot); free(scratch); free(dig);
 }
 
-/* FFT-route PBS over a batch, OpenMP across ciphertexts (the "port" CPU baseline).
- * Returns the number of threads used. */
+/* FFT-route PBS over a batch (the "port" CPU baseline).  OpenMP over GROUPS of up to ORC_GROUP ciphertexts: a group
+ * is keyswitched together (every KSK row is read once per group) and blind-rotated in lockstep (every 64 KiB Fourier
+ * GGSW is read once per group), so the 58 MB + 46 MB of key material a PBS touches stream from memory once per
+ * group instead of once per ciphertext -- with all cores busy the per-ciphertext form is DRAM-bound.  Same
+ * arithmetic per ciphertext as orc_keyswitch + orc_blind_rotate_fft (identical words).  Returns the threads used. */
+#define ORC_GROUP 4
 int orc_pbs_fft_batch(const orc_params *p, const double *fbsk, const u64 *ksk, const u64 *luts,
                       const int32_t *lut_ids, const u64 *in, int count, u64 *out) {
     int threads = 1;
+    const int n = p->n, N = p->N, Nb = p->N * p->k, L = p->ks_level, lg = ilog2(2 * N);
+    const int groups = (count + ORC_GROUP - 1) / ORC_GROUP;
 #pragma omp parallel
     {
 #ifdef _OPENMP
 #pragma omp single
         threads = omp_get_num_threads();
 #endif
-        fft_plan *pl = orc_fft_plan_new(p->N);
-        u64 *ks = (u64 *)malloc(sizeof(u64) * (p->n + 1));
-        u64 *acc = (u64 *)malloc(sizeof(u64) * 2 * p->N);
+        fft_plan *pl = orc_fft_plan_new(N);
+        u64 *ks = (u64 *)malloc(sizeof(u64) * ORC_GROUP * (n + 1));
+        u64 *acc = (u64 *)malloc(sizeof(u64) * ORC_GROUP * 2 * N);
+        u64 *rot = (u64 *)malloc(sizeof(u64) * 2 * N);
+        double *scratch = (double *)malloc(sizeof(double) * 4 * N);
+        i64 *dig = (i64 *)malloc(sizeof(i64) * N);
+        i64 digits[64];
+        const size_t ggsw_sz = (size_t)p->pbs_level * 4 * N;
 #pragma omp for schedule(dynamic, 1)
-        for (int b = 0; b < count; b++) {
-            orc_keyswitch(p, ksk, in + (size_t)b * (p->N + 1), ks);
-            orc_blind_rotate_fft(p, pl, fbsk, ks, luts + (size_t)lut_ids[b] * p->N, acc);
-            orc_sample_extract(p->N, acc, out + (size_t)b * (p->N + 1));
+        for (int g = 0; g < groups; g++) {
+            const int b0 = g * ORC_GROUP, gc = (count - b0 < ORC_GROUP) ? count - b0 : ORC_GROUP;
+            /* keyswitch, KSK rows outermost */
+            for (int q = 0; q < gc; q++) {
+                u64 *o = ks + (size_t)q * (n + 1);
+                for (int c = 0; c < n; c++) o[c] = 0;
+                o[n] = in[(size_t)(b0 + q) * (Nb + 1) + Nb];
+            }
+            for (int i = 0; i < Nb; i++)
+                for (int q = 0; q < gc; q++) {
+                    decompose(in[(size_t)(b0 + q) * (Nb + 1) + i], p->ks_base_log, L, digits);
+                    for (int lvl = 1; lvl <= L; lvl++) {
+                        const u64 d = (u64)digits[lvl - 1];
+                        if (!d) continue;
+                        sub_scaled_row(ks + (size_t)q * (n + 1), ksk + ((size_t)i * L + (lvl - 1)) * (n + 1), d, n + 1);
+                    }
+                }
+            /* blind rotation, CMUX steps outermost */
+            for (int q = 0; q < gc; q++) {
+                u64 *a = acc + (size_t)q * 2 * N;
+                const u32 bt = modswitch(ks[(size_t)q * (n + 1) + n], lg) % (2 * N);
+                memset(a, 0, sizeof(u64) * N);
+                monomial_mul(a + N, luts + (size_t)lut_ids[b0 + q] * N, (2 * N - bt) % (2 * N), N);
+            }
+            for (int i = 0; i < n; i++)
+                for (int q = 0; q < gc; q++) {
+                    u64 *a = acc + (size_t)q * 2 * N;
+                    const u32 at = modswitch(ks[(size_t)q * (n + 1) + i], lg) % (2 * N);
+                    if (at == 0) continue;
+                    for (int r = 0; r < 2; r++) {
+                        monomial_mul(rot + r * N, a + r * N, at, N);
+                        for (int j = 0; j < N; j++) rot[r * N + j] -= a[r * N + j];
+                    }
+                    external_product_fft(p, pl, fbsk + i * ggsw_sz, rot, a, scratch, dig);
+                }
+            for (int q = 0; q < gc; q++) orc_sample_extract(N, acc + (size_t)q * 2 * N, out + (size_t)(b0 + q) * (N + 1));
         }
-        free(ks); free(acc); orc_fft_plan_free(pl);
+        free(ks); free(acc); free(rot); free(scratch); free(dig); orc_fft_plan_free(pl);
     }
     return threads;
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the bench sets the thread count explicitly.  Returns the
+ * count in effect. */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 int orc_max_threads(void) {

@@ -24,7 +24,7 @@ def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
         subprocess.check_call(
-            ["gcc", "-O3", "-fopenmp", "-shared", "-fPIC", "-std=gnu11", "-o", _LIB, _SRC, "-lm"]
+            ["gcc", "-O3", "-fno-math-errno", "-fno-trapping-math", "-fopenmp", "-shared", "-fPIC", "-std=gnu11", "-o", _LIB, _SRC, "-lm"]
         )
     return _LIB
 
@@ -85,6 +85,10 @@ class Oracle:
 
     def max_threads(self) -> int:
         return int(self.lib.orc_max_threads())
+
+    def set_threads(self, n: int) -> int:
+        """OpenMP thread count for the batch entry points (torchrun exports OMP_NUM_THREADS=1); returns the count in effect"""
+        return int(self.lib.orc_set_threads(C.c_int(int(n))))
 
     # ---- keys / client side
     def keygen(self, seed: int, want_bsk=True, want_ksk=True) -> Keys:

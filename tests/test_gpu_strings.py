@@ -233,3 +233,29 @@ def test_every_arena_block_matches_the_plaintext_interpretation(keys):
         written = np.array([int(j["dst"]) for j in jobs], np.int64)
         assert np.array_equal(got[written], plain[written] % 16), method
         g.close()
+
+
+@pytest.mark.parametrize("fast", [True, False], ids=["fast", "reference_op_order"])
+def test_config1_cli_all_52_methods(keys, fast):
+    """BASELINE config 1: `fhestring --string hello --pattern ello --n 1 --from ello --to _llo`, every algorithm the
+    CLI runs (/root/reference/src/main.rs:47-115: 52 methods, the 18 *_clear forms included, in the CLI's order), each
+    result bit-exact against Rust std AND against the plaintext restatement of the reference's algorithm"""
+    from cli_config1 import METHODS, run_all
+    ck, sk, pp = keys
+    sk.fast = fast
+    try:
+        rows = run_all(ck, sk, pp, "hello", "ello", 1, "ello", "_llo")
+    finally:
+        sk.fast = True
+    assert [r["method"] for r in rows] == METHODS
+    bad = [(r["method"], r["got"], r["std"], r["oracle"]) for r in rows if not r["passed"]]
+    assert not bad, bad
+
+
+def test_config1_cli_second_input_set(keys):
+    """the same loop on inputs where the pattern occurs twice, n = 2 and from/to differ in length"""
+    from cli_config1 import run_all
+    ck, sk, pp = keys
+    rows = run_all(ck, sk, pp, "a bc bc d", "bc", 2, "bc", "xyz")
+    bad = [(r["method"], r["got"], r["std"], r["oracle"]) for r in rows if not r["passed"]]
+    assert not bad, bad

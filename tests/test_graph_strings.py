@@ -418,3 +418,40 @@ def test_random_expression_dags_of_char_primitives(Graph):
         values = run_program(g, slots.reshape(-1), blocks_of(vals).reshape(-1))
         got = chars_of(values, g.char_slots([n for n, _ in outs]))
         assert [int(v) for v in got] == [v for _, v in outs], trial
+
+
+# ---- operands that occur more than once: identical chars share one node, so a lazy sum can carry a
+# coefficient m > 1 on ONE PBS output and its noise counts m^2 -- the recording must stay inside the budget
+@pytest.mark.parametrize("s", ["h", "hi", "abc", "hell", "hello", "hello!"])
+def test_repeat_clear_up_to_max_repetitions(Graph, s):
+    for n in range(4, 17):                                   # the reference CLI allows n up to 16 (main.rs:17)
+        enc = [[ord(ch) for ch in s] + [0], n]
+        got, _ = run_method(Graph, "repeat_clear", enc, 1)
+        assert list(got) == list(P.repeat_clear(*enc)), (s, n)
+
+
+@pytest.mark.parametrize("method", ["lt", "le", "gt", "ge", "eq", "ne"])
+def test_string_compared_with_itself(Graph, method):
+    vals = [ord(ch) for ch in "hello"] + [0]
+    g = Graph()
+    ids, slots = g.input_chars(len(vals))
+    _, rc = g.string_op(method, [ids, ids], fast=True)       # the SAME FheString on both sides
+    g.mark_output([rc])
+    g.compile(1)
+    values = run_program(g, slots.reshape(-1), blocks_of(vals).reshape(-1))
+    want = {"lt": 0, "le": 1, "gt": 0, "ge": 1, "eq": 1, "ne": 0}[method]
+    assert int(chars_of(values, g.char_slots([rc]))[0]) == want
+
+
+@pytest.mark.parametrize("n", [4, 7, 16])
+def test_repeat_with_trivial_count(Graph, n):
+    vals = [ord(ch) for ch in "ab"] + [0]
+    g = Graph()
+    ids, slots = g.input_chars(len(vals))
+    nid = g.trivial_chars([n])
+    rs, _ = g.string_op("repeat", [ids, nid], fast=True)
+    g.mark_output(list(rs))
+    g.compile(1)
+    values = run_program(g, slots.reshape(-1), blocks_of(vals).reshape(-1))
+    got = [int(v) for v in chars_of(values, g.char_slots(list(rs)))]
+    assert got == list(P.repeat(vals, n))
