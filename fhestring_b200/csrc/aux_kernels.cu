@@ -12,7 +12,10 @@ __global__ void lut_poly_kernel(const uint8_t* table, int entries, int delta_log
     if (j >= kN) return;
     const int box = kN / entries;
     const int m = (j + box / 2) & (kN - 1);
-    const u64 v = ((u64)table[m / box]) << delta_log;
+    const uint8_t e = table[m / box];
+    // a half-step table (fhestr_lut_register: entries 0x80 | e) holds e - 1/2; the engine adds the 1/2 back after the
+    // sample extract, so the negacyclic half reads 1 - e
+    const u64 v = (e & 0x80) ? (((u64)(e & 0x7f)) << delta_log) - ((u64)1 << (delta_log - 1)) : ((u64)e) << delta_log;
     out[j] = (m < box / 2) ? (u64)0 - v : v;
 }
 int launch_lut_poly(const uint8_t* table_dev, int entries, int delta_log, u64* out, cudaStream_t s) {

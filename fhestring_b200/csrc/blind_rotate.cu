@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     job.ks = A.ks + (size_t)b * (A.n + 1);
     const int lut = A.jobs ? A.jobs[b].lut : A.lut_ids[b];
     job.lut = A.luts + (size_t)lut * kN;
+    job.post = A.lut_post ? A.lut_post[lut] : 0;
     job.init_acc = A.init_acc ? A.init_acc + (size_t)b * 2 * kN : nullptr;
     job.out_acc = A.out_acc ? A.out_acc + (size_t)b * 2 * kN : nullptr;
     job.out_lwe = A.jobs ? A.arena + (size_t)A.jobs[b].dst * (kN + 1) : nullptr;

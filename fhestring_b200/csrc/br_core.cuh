@@ -333,6 +333,7 @@ struct BrJobView {
     // result everywhere at once, so no collective follows the kernel
     u64* out_lwe_peer[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_peers = 0;
+    u64 post = 0;         // added to the body of the extracted LWE (half-step LUTs: + delta/2, see fhestr_lut_register)
 };
 
 constexpr int kMaxPeers = 7;
@@ -379,8 +380,8 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
                 for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][j] = w;
             }
         } else if (t == 0) {
-            job.out_lwe[kN] = acc_to_u64(acc[0]);
-            for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][kN] = acc_to_u64(acc[0]);
+            job.out_lwe[kN] = acc_to_u64(acc[0]) + job.post;
+            for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][kN] = acc_to_u64(acc[0]) + job.post;
         }
     }
 }

@@ -336,7 +336,7 @@ FHE_HD void wide_thread_main(Ctx& c, const BrJobView& job, const WideConsts& K) 
             for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][j] = w;
         }
         if (t == 0) {
-            const u64 b = acc_to_u64(c.acc(1)[0]);
+            const u64 b = acc_to_u64(c.acc(1)[0]) + job.post;
             job.out_lwe[kN] = b;
             for (int r = 0; r < job.n_peers; r++) job.out_lwe_peer[r][kN] = b;
         }

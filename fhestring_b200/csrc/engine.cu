@@ -38,6 +38,7 @@ struct fhestr_engine {
     int n_sms = 148;
     bool keys_loaded = false;
     u64* luts = nullptr;
+    u64* lut_post = nullptr;           // [cap_luts]: delta/2 for half-step tables, else 0
     int n_luts = 0, cap_luts = 256;
     std::vector<std::vector<uint8_t>> lut_tables;   // host copy: identical tables share one id
     // per-batch scratch (grown on demand)
@@ -237,6 +238,8 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
     CKC(cudaMalloc(&e->bsk_w, (size_t)p->n * kWKeyTile * sizeof(cplx)));
     CKC(blind_rotate_wide_configure());
     CKC(cudaMalloc(&e->luts, (size_t)e->cap_luts * kN * sizeof(u64)));
+    CKC(cudaMalloc(&e->lut_post, (size_t)e->cap_luts * sizeof(u64)));
+    CKC(cudaMemsetAsync(e->lut_post, 0, (size_t)e->cap_luts * sizeof(u64), e->stream));
     CKC(cudaMalloc(&e->bsk_f, (size_t)p->n * kBskStepElems * sizeof(cplx)));
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
     CKC(cudaMalloc(&e->ksk_corr, (size_t)(p->n + 1) * sizeof(u64)));
@@ -261,7 +264,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
     cudaFree(e->bsk_w); cudaFree(e->wide_tab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
-    cudaFree(e->luts); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
+    cudaFree(e->luts); cudaFree(e->lut_post); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -316,6 +319,12 @@ int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id)
     CK(cudaSetDevice(e->device));
     const int entries = 1 << (63 - e->prm.delta_log);
     const std::vector<uint8_t> key(table, table + entries);
+    int flagged = 0;
+    for (int i = 0; i < entries; i++) {
+        flagged += (table[i] & 0x80) ? 1 : 0;
+        if ((table[i] & 0x7f) >= entries) return fail(e, FHESTR_E_INVALID, "LUT entry outside the block's value range");
+    }
+    if (flagged && flagged != entries) return fail(e, FHESTR_E_INVALID, "a half-step LUT must flag every entry with 0x80");
     for (int i = 0; i < e->n_luts; i++)
         if (e->lut_tables[i] == key) { *lut_id = i; return FHESTR_OK; }
     if (e->n_luts >= e->cap_luts) {  // grow the registry (ids stay valid)
@@ -325,12 +334,21 @@ int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id)
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaFree(e->luts));
         e->luts = bigger;
+        u64* bigger_post = nullptr;
+        CK(cudaMalloc(&bigger_post, (size_t)e->cap_luts * 2 * sizeof(u64)));
+        CK(cudaMemsetAsync(bigger_post, 0, (size_t)e->cap_luts * 2 * sizeof(u64), e->stream));
+        CK(cudaMemcpyAsync(bigger_post, e->lut_post, (size_t)e->n_luts * sizeof(u64), cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaFree(e->lut_post));
+        e->lut_post = bigger_post;
         e->cap_luts *= 2;
     }
     int rc = stage_bytes(e, table, entries);
     if (rc) return rc;
     e->launches += launch_lut_poly(e->d_bytes, entries, e->prm.delta_log, e->luts + (size_t)e->n_luts * kN, e->stream);
     CK(cudaGetLastError());
+    const u64 post = flagged ? (u64)1 << (e->prm.delta_log - 1) : 0;
+    CK(cudaMemcpyAsync(e->lut_post + e->n_luts, &post, sizeof post, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));  // d_bytes is reused by the next call
     e->lut_tables.push_back(key);
     *lut_id = e->n_luts++;
@@ -404,7 +422,7 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         e->launches += e->ks_path == 0 ? launch_keyswitch_mma(ks, e->stream) : launch_keyswitch(ks, e->stream);
         if (e->timing) CK(cudaEventRecord(t.b, e->stream));
         BrBatchArgs br{};
-        br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
+        br.ks = e->ks_out; br.luts = e->luts; br.lut_post = e->lut_post; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
         br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
         br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
         br.n_peers = 0;

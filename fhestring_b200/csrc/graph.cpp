@@ -165,8 +165,11 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     };
     uint32_t S = vset_of(ops, cst) & vset_of(atom_ops(), c);
     if (!S) S = vset_of(atom_ops(), c);
-    if (S >> 16 & 1) fail("PBS input can reach the ambiguous value 16");
-    if (!signed_ok && (S >> 16)) {
+    // half-step tables (entries 0x80 | e, fhestr_lut_register): f(v) = e[v] below 16, 1 - e[v - 16] from 16 on; they
+    // are MEANT to be read on [16, 32) (threshold of a sum), so the padding-bit checks do not apply to them
+    const bool half = (table[0] & 0x80) != 0;
+    if (!half && (S >> 16 & 1)) fail("PBS input can reach the ambiguous value 16");
+    if (!half && !signed_ok && (S >> 16)) {
         std::string m = "PBS input overflows into the padding bit:";
         for (auto& op : ops) m += " (" + std::to_string(op.second) + " x vset " + std::to_string(nodes[op.first].vset) + ")";
         fail(m + " + " + std::to_string(cst));
@@ -175,7 +178,8 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     uint32_t O = 0;
     for (int v = 0; v < 32; v++) {
         if (!(S >> v & 1)) continue;
-        O |= 1u << (v < 16 ? table[v] : mod32(-(int)table[v - 16]));
+        if (half) O |= 1u << (v < 16 ? (table[v] & 0x7f) : mod32(1 - (int)(table[v - 16] & 0x7f)));
+        else O |= 1u << (v < 16 ? table[v] : mod32(-(int)table[v - 16]));
     }
     if (popcount32(O) == 1) return trivial_block(__builtin_ctz(O));
 
@@ -225,7 +229,7 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
         cst = c;
         flatten(ops, cst, terms, c);
     }
-    if (terms.empty()) return trivial_block(table[c & 15] * (c < 16 ? 1 : -1));
+    if (terms.empty()) return trivial_block(half ? (c < 16 ? (table[c] & 0x7f) : 1 - (int)(table[c - 16] & 0x7f)) : table[c & 15] * (c < 16 ? 1 : -1));
 
     const int lid = lut_id(table);
     std::string key;
@@ -415,17 +419,17 @@ Char Graph::flip(const Char& a) { return sub(trivial_char(1), a); }
 
 // ---- wide reductions (plaintext-identical to chains of bitand / bitor / add on 0/1 chars)
 static const int kChunk = 15;
-
-// chunk sizes of a balanced reduction tree with fan-in <= kChunk: n inputs in ceil(n / kChunk) nearly equal chunks
-// -- except when one input is left over after full chunks (n = 16, 31, ...): it passes through as a chunk of one, which
-// saves a PBS at the same depth (16 nibble flags of an 8-char window: one PBS of 15 + the 16th flag, not two of 8)
-static std::vector<size_t> balanced_chunks(size_t n) {
-    if (n > 1 && n % kChunk == 1) {
-        std::vector<size_t> sizes(n / kChunk, (size_t)kChunk);
-        sizes.push_back(1);
-        return sizes;
-    }
-    const size_t c = (n + kChunk - 1) / kChunk;
+// AND / OR of up to 16 flags in ONE PBS: the half-step table with e = 0 everywhere is the threshold [x >= 16]
+// (its negacyclic half reads 1 - e), so  AND_k = [sum + (16 - k) >= 16]  and  OR = [sum + 15 >= 16].  A 16-entry
+// table of whole steps cannot do either for 16 flags (17 different sums), which cost one more dependency level.
+static const int kFan = 16;
+static std::array<uint8_t, 16> threshold_table() {
+    std::array<uint8_t, 16> t;
+    t.fill(0x80);
+    return t;
+}
+static std::vector<size_t> fan_chunks(size_t n) {
+    const size_t c = (n + kFan - 1) / kFan;
     std::vector<size_t> sizes(c, n / c);
     for (size_t i = 0; i < n % c; i++) sizes[i]++;
     return sizes;
@@ -439,84 +443,63 @@ static void dedupe(std::vector<BlockId>& v) {
     v.swap(out);
 }
 
-Char Graph::and_all(const std::vector<Char>& flags) {
-    std::vector<BlockId> cur;
-    for (auto& c : flags) cur.push_back(cond_bit(c));
+BlockId Graph::and_flags(std::vector<BlockId> cur) {
     dedupe(cur);
-    if (cur.empty()) return trivial_char(1);
+    if (cur.empty()) return trivial_block(1);
     while (cur.size() > 1) {
         std::vector<BlockId> nxt;
         size_t i = 0;
-        for (size_t k : balanced_chunks(cur.size())) {
+        for (size_t k : fan_chunks(cur.size())) {
             if (k == 1) { nxt.push_back(cur[i++]); continue; }
             std::vector<std::pair<BlockId, int>> ops;
             for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
-            nxt.push_back(pbs(ops, 0, table_of([k](int v) { return v == (int)k; })));
+            nxt.push_back(pbs(ops, kFan - (int)k, threshold_table()));
             i += k;
         }
         cur.swap(nxt);
     }
-    return flag_char(cur[0]);
+    return cur[0];
+}
+
+BlockId Graph::or_flags(std::vector<BlockId> cur) {
+    dedupe(cur);
+    if (cur.empty()) return trivial_block(0);
+    while (cur.size() > 1) {
+        std::vector<BlockId> nxt;
+        size_t i = 0;
+        for (size_t k : fan_chunks(cur.size())) {
+            if (k == 1) { nxt.push_back(cur[i++]); continue; }
+            std::vector<std::pair<BlockId, int>> ops;
+            for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
+            nxt.push_back(pbs(ops, kFan - 1, threshold_table()));
+            i += k;
+        }
+        cur.swap(nxt);
+    }
+    return cur[0];
+}
+
+Char Graph::and_all(const std::vector<Char>& flags) {
+    std::vector<BlockId> cur;
+    for (auto& c : flags) cur.push_back(cond_bit(c));
+    return flag_char(and_flags(cur));
 }
 
 Char Graph::or_all(const std::vector<Char>& flags) {
     std::vector<BlockId> cur;
     for (auto& c : flags) cur.push_back(cond_bit(c));
-    dedupe(cur);
-    if (cur.empty()) return trivial_char(0);
-    while (cur.size() > 1) {
-        std::vector<BlockId> nxt;
-        size_t i = 0;
-        for (size_t k : balanced_chunks(cur.size())) {
-            if (k == 1) { nxt.push_back(cur[i++]); continue; }
-            std::vector<std::pair<BlockId, int>> ops;
-            for (size_t j = 0; j < k; j++) ops.push_back({cur[i + j], 1});
-            nxt.push_back(pbs(ops, 0, table_of([](int v) { return v != 0; })));
-            i += k;
-        }
-        cur.swap(nxt);
-    }
-    return flag_char(cur[0]);
+    return flag_char(or_flags(cur));
 }
 
-// OR over windows of (AND over the window's flags), one level shallower than or_all(and_all(.)) when a window
-// reduces to two partial flags: two windows share one PBS on (a + b) + 4 (a' + b') -- both sums lie in {0,1,2},
-// the LUT fires when either is 2 (noise2 = 1 + 1 + 16 + 16 = 34, the reference's own worst case)
+// OR over windows of (AND over the window's flags): one level per 16-fold of each (contains over 8-char windows: the
+// 16 nibble flags of a window are ONE threshold PBS, 250 windows are 16 + 1 more)
 Char Graph::or_of_ands(const std::vector<std::vector<BlockId>>& windows) {
-    std::vector<std::vector<BlockId>> w = windows;
-    bool all_two = !w.empty();
-    for (auto& flags : w) {
-        dedupe(flags);
+    std::vector<BlockId> w;
+    for (auto& flags : windows) {
         if (flags.empty()) return trivial_char(1);   // an empty AND is true
-        while (flags.size() > 2) {
-            std::vector<BlockId> nxt;
-            size_t i = 0;
-            for (size_t k : balanced_chunks(flags.size())) {
-                if (k == 1) { nxt.push_back(flags[i++]); continue; }
-                std::vector<std::pair<BlockId, int>> ops;
-                for (size_t j = 0; j < k; j++) ops.push_back({flags[i + j], 1});
-                nxt.push_back(pbs(ops, 0, table_of([k](int v) { return v == (int)k; })));
-                i += k;
-            }
-            flags.swap(nxt);
-        }
-        all_two = all_two && flags.size() == 2;
+        w.push_back(and_flags(flags));
     }
-    std::vector<Char> terms;
-    if (all_two) {
-        auto pair_tab = table_of([](int v) { return (int)(((v & 3) == 2) || ((v >> 2) == 2)); });
-        auto single_tab = table_of([](int v) { return (int)(v == 2); });
-        for (size_t i = 0; i + 1 < w.size(); i += 2)
-            terms.push_back(flag_char(pbs({{w[i][0], 1}, {w[i][1], 1}, {w[i + 1][0], 4}, {w[i + 1][1], 4}}, 0, pair_tab)));
-        if (w.size() % 2) terms.push_back(flag_char(pbs({{w.back()[0], 1}, {w.back()[1], 1}}, 0, single_tab)));
-    } else {
-        for (auto& flags : w) {
-            std::vector<Char> f;
-            for (auto b : flags) f.push_back(flag_char(b));
-            terms.push_back(and_all(f));
-        }
-    }
-    return or_all(terms);
+    return flag_char(or_flags(w));
 }
 
 // column compression: each column holds blocks of weight 4^c; chunks whose maximum sum is <= 15 are

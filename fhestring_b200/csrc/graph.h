@@ -98,8 +98,10 @@ public:
     Char is_lowercase(const Char& a);                 // :146
     Char flip(const Char& a);                         // :161
     // plaintext-equivalent wide reductions used by the depth-minimised string algorithms
-    Char and_all(const std::vector<Char>& flags);     // AND of 0/1 chars, tree of sum + is_k LUTs
-    Char or_all(const std::vector<Char>& flags);      // OR  of 0/1 chars, tree of sum + nz LUTs
+    Char and_all(const std::vector<Char>& flags);     // AND of 0/1 chars, tree of sum + threshold LUTs (fan-in 16)
+    Char or_all(const std::vector<Char>& flags);      // OR  of 0/1 chars, tree of sum + threshold LUTs (fan-in 16)
+    BlockId and_flags(std::vector<BlockId> flags);    // the same on 0/1 blocks
+    BlockId or_flags(std::vector<BlockId> flags);
     Char sum_flags(const std::vector<Char>& flags);   // u8 sum (mod 256) of 0/1 chars
     Char nonzero(const Char& a);                      // a != 0 as one PBS over the block sum
     Char block_and_eq(const std::vector<std::pair<Char, Char>>& pairs);  // AND_i (a_i == b_i), nibble level

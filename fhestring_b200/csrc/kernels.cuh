@@ -12,6 +12,7 @@ namespace fhestr {
 struct BrBatchArgs {
     const u64* ks;            // [B][n+1] keyswitched LWEs
     const u64* luts;          // [n_luts][N] body polynomials
+    const u64* lut_post;      // [n_luts] constant added to the body of the extracted LWE (half-step tables), or nullptr
     const int32_t* lut_ids;   // [B] (one per job; taken from jobs when jobs != nullptr)
     const fhestr_job* jobs;   // [B] device job list (dst + lut) or nullptr
     u64* arena;               // [blocks][N+1]

@@ -81,7 +81,11 @@ void* fhestr_arena_ptr(fhestr_engine* e);                /* device pointer, for 
 int fhestr_load_keys(fhestr_engine* e, const uint64_t* bsk_std, const uint64_t* ksk);
 
 /* ---- LUT registry (replaces generate_lookup_table; kernel K5) ---------------------------------- */
-/* table has 2^(63-delta_log) entries (16): f(x) over the 4-bit block value */
+/* table has 2^(63-delta_log) entries (16): f(x) over the 4-bit block value.  A block whose value v carries the padding
+ * bit (v in [16, 32)) reads -f(v - 16) (negacyclic).  HALF-STEP tables: every entry given as 0x80 | e stands for
+ * e - 1/2, and the engine adds the 1/2 back to the result, so f(v) = e[v] for v < 16 and 1 - e[v - 16] for
+ * v in [16, 32): with e = 0 everywhere that is the threshold [v >= 16], which turns an AND or an OR over 16 flags
+ * (sum + constant) into ONE PBS. */
 int fhestr_lut_register(fhestr_engine* e, const uint8_t* table, int32_t* lut_id);
 int fhestr_lut_download(fhestr_engine* e, int32_t lut_id, uint64_t* out_poly /* [N] */);
 

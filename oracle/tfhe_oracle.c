@@ -260,7 +260,9 @@ void orc_lut_poly(int N, const u8 *table, int delta_log, u64 *out) {
     const int box = N / entries;
     u64 *tmp = (u64 *)malloc(sizeof(u64) * N);
     for (int i = 0; i < entries; i++)
-        for (int j = 0; j < box; j++) tmp[i * box + j] = ((u64)table[i]) << delta_log;
+        for (int j = 0; j < box; j++)   /* half-step tables (0x80 | e) hold e - 1/2; the caller adds 1/2 to the result */
+            tmp[i * box + j] = (table[i] & 0x80) ? (((u64)(table[i] & 0x7f)) << delta_log) - ((u64)1 << (delta_log - 1))
+                                                  : ((u64)table[i]) << delta_log;
     for (int j = 0; j < box / 2; j++) tmp[j] = (u64)0 - tmp[j];
     for (int j = 0; j < N; j++) out[j] = tmp[(j + box / 2) % N]; /* rotate left by box/2 */
     free(tmp);

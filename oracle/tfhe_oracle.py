@@ -156,6 +156,11 @@ class Oracle:
         self.lib.orc_lut_poly(C.c_int(self.p.N), _p(t, C.c_uint8), C.c_int(self.p.delta_log), _p(out, C.c_uint64))
         return out
 
+    def lut_post(self, table) -> int:
+        """the constant added to the body of a PBS result: delta/2 for a half-step table (entries 0x80 | e stand for
+        e - 1/2; include/fhestr_engine.h, fhestr_lut_register), else 0"""
+        return (1 << (self.p.delta_log - 1)) if (int(np.asarray(table)[0]) & 0x80) else 0
+
     def blind_rotate_exact(self, keys: Keys, ks_ct: np.ndarray, lut: np.ndarray) -> np.ndarray:
         acc = np.zeros((2, self.p.N), np.uint64)
         self.lib.orc_blind_rotate_exact(C.byref(self.p), _p(keys.bsk, C.c_uint64),
@@ -185,7 +190,14 @@ class Oracle:
                                           _p(np.ascontiguousarray(glwe), C.c_uint64), _p(acc, C.c_uint64))
         return acc
 
-    def pbs_exact(self, keys: Keys, luts: np.ndarray, lut_ids, cts: np.ndarray) -> np.ndarray:
+    @staticmethod
+    def _add_post(out, ids, post):
+        if post is not None:
+            with np.errstate(over="ignore"):
+                out[:, -1] += np.asarray(post, np.uint64)[np.asarray(ids, np.int64)]
+        return out
+
+    def pbs_exact(self, keys: Keys, luts: np.ndarray, lut_ids, cts: np.ndarray, post=None) -> np.ndarray:
         cts = np.ascontiguousarray(cts, np.uint64).reshape(-1, self.big)
         luts = np.ascontiguousarray(luts, np.uint64).reshape(-1, self.p.N)
         ids = np.ascontiguousarray(lut_ids, np.int32)
@@ -193,9 +205,9 @@ class Oracle:
         self.lib.orc_pbs_exact_batch(C.byref(self.p), _p(keys.bsk, C.c_uint64), _p(keys.ksk, C.c_uint64),
                                      _p(luts, C.c_uint64), _p(ids, C.c_int32), _p(cts, C.c_uint64),
                                      C.c_int(cts.shape[0]), _p(out, C.c_uint64))
-        return out
+        return self._add_post(out, ids, post)
 
-    def pbs_fft(self, keys: Keys, fbsk: np.ndarray, luts: np.ndarray, lut_ids, cts: np.ndarray):
+    def pbs_fft(self, keys: Keys, fbsk: np.ndarray, luts: np.ndarray, lut_ids, cts: np.ndarray, post=None):
         """f64-FFT PBS (tfhe-rs' own route), OpenMP across ciphertexts.  Returns (out, threads)."""
         cts = np.ascontiguousarray(cts, np.uint64).reshape(-1, self.big)
         luts = np.ascontiguousarray(luts, np.uint64).reshape(-1, self.p.N)
@@ -204,4 +216,4 @@ class Oracle:
         th = self.lib.orc_pbs_fft_batch(C.byref(self.p), _p(fbsk, C.c_double), _p(keys.ksk, C.c_uint64),
                                         _p(luts, C.c_uint64), _p(ids, C.c_int32), _p(cts, C.c_uint64),
                                         C.c_int(cts.shape[0]), _p(out, C.c_uint64))
-        return out, int(th)
+        return self._add_post(out, ids, post), int(th)

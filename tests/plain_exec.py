@@ -26,9 +26,13 @@ def run_jobs(values: np.ndarray, jobs, luts, delta_log: int = 59):
         if lut < 0:
             values[int(j["dst"])] = v
         else:
-            assert v != 16, "PBS input reached the ambiguous value 16"
-            f = int(luts[lut][v & 15])
-            values[int(j["dst"])] = f if v < 16 else (-f) % 32
+            e = int(luts[lut][v & 15])
+            if e & 0x80:       # half-step table: f(v) = e[v] below 16, 1 - e[v - 16] from 16 on (fhestr_lut_register)
+                e &= 0x7f
+                values[int(j["dst"])] = e if v < 16 else (1 - e) % 32
+            else:
+                assert v != 16, "PBS input reached the ambiguous value 16"
+                values[int(j["dst"])] = e if v < 16 else (-e) % 32
 
 
 def run_program(graph, input_slots, input_blocks, values=None):

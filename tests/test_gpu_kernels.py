@@ -2,9 +2,10 @@
 
 Bars (north star): keyswitch, mod-switch + sample extract and LUT generation bit-exact at the
 ciphertext level; blind rotation within a stated torus tolerance per coefficient (single external
-product: RMS <= 2^-24, max <= 2^-21 of the torus against exact integer arithmetic; the CPU f64 route
+product: RMS <= 2^-25.1, max <= 2^-22.5 of the torus against exact integer arithmetic; the CPU f64 route
 measures RMS 2^-25.7 on the same inputs); decrypted results identical; output noise variance inside the
-parameter set's budget (analytic 4.5e-10)."""
+parameter set's budget (analytic 4.5e-10).  The K3 bounds are 1.5 x (RMS) and 1.25 x (variance) what the CPU
+f64 route measures on the same kind of input; every GPU run appends its measured figures to gpurun_out/k3_accuracy.jsonl."""
 import os
 
 import numpy as np
@@ -168,9 +169,12 @@ def test_single_external_product_tolerance(build_lib, small_oracle, br_mode):
         if e == 0:
             assert not d.any()  # nothing to add (the throughput kernel skips the step, the latency kernel adds 0)
             continue
-        # RMS <= 2^-24, max <= 2^-21 of the torus (f64 FFT round-off + the 2^-33 rounding to acc_t)
-        assert np.sqrt(np.mean(d * d)) <= 2.0**40, (e, np.log2(np.sqrt(np.mean(d * d))))
-        assert np.abs(d).max() <= 2.0**43, (e, np.log2(np.abs(d).max()))
+        # Bound: 1.5 x what the CPU f64 route measures on such inputs (RMS 2^-25.7 of the torus: SURVEY.md 8d), i.e.
+        # RMS <= 2^-25.1; max <= 2^-22.5 (4096 coefficients: about 6 sigma).  Measured on B200 (profiles/
+        # r2_k3_accuracy.md): throughput kernel RMS 2^-25.5 / max 2^-23.1, latency kernel 2^-25.6 / 2^-23.4 -- f64 FFT
+        # round-off plus the 2^-33 rounding of the 32-bit accumulator, which is 200 x below it.
+        assert np.sqrt(np.mean(d * d)) <= 2.0**(64 - 25.1), (e, np.log2(np.sqrt(np.mean(d * d))) - 64)
+        assert np.abs(d).max() <= 2.0**(64 - 22.5), (e, np.log2(np.abs(d).max()) - 64)
         _record("external_product", dict(kernel=br_mode, e=e, log2_rms_torus=float(np.log2(np.sqrt(np.mean(d * d))) - 64),
                                          log2_max_torus=float(np.log2(np.abs(d).max()) - 64)))
     eng.close()
@@ -194,6 +198,40 @@ def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, br_mod
     dec = o.decrypt_big(keys, small_engine.download(500, B))
     want = [(tables[i // 32][v % 16] * (1 if v < 16 else -1)) % 16 for i in range(B) for v in [i % 32]]
     assert np.array_equal(dec, np.array(want))
+    small_engine.set_br_mode(0)
+
+
+@pytest.mark.parametrize("br_mode", [1, 2], ids=["throughput_kernel", "latency_kernel"])
+def test_half_step_table_threshold_and_or(small_engine, small_oracle, br_mode):
+    """K5 + K4 for half-step tables (entries 0x80 | e = e - 1/2, the engine adds 1/2 back to the extracted body): the
+    polynomial is bit-exact against the oracle, all 32 block values decrypt to [v >= 16], and an AND and an OR over 16
+    encrypted flags are ONE PBS each on sum + constant"""
+    from fhestring_b200.engine import make_jobs, single_term_jobs
+    o, keys = small_oracle
+    small_engine.set_br_mode(br_mode)
+    thr = [0x80] * 16
+    lid = small_engine.lut(thr)
+    assert np.array_equal(small_engine.lut_download(lid), o.lut_poly(thr))
+    vals = np.arange(32)
+    small_engine.upload(0, o.encrypt_big(keys, vals, seed=41))
+    small_engine.pbs_batch(single_term_jobs(600 + np.arange(32), np.arange(32), lid))
+    assert np.array_equal(o.decrypt_big(keys, small_engine.download(600, 32)), (vals >= 16).astype(np.int64))
+    # 16 flags per row: AND = [sum + 0 >= 16], OR = [sum + 15 >= 16]
+    rng = np.random.default_rng(5)
+    flags = rng.integers(0, 2, (8, 16))
+    flags[0] = 1; flags[1] = 0; flags[2] = 1; flags[2, 7] = 0; flags[3] = 0; flags[3, 11] = 1
+    small_engine.upload(100, o.encrypt_big(keys, flags.reshape(-1), seed=42))
+    jobs = make_jobs(16)
+    for r in range(8):
+        for kind in range(2):
+            j = jobs[2 * r + kind]
+            j["dst"] = 700 + 2 * r + kind; j["lut"] = lid; j["n_terms"] = 16
+            j["src"][:] = 100 + 16 * r + np.arange(16); j["coeff"][:] = 1
+            j["constant"] = (15 << 59) if kind else 0
+    small_engine.pbs_batch(jobs)
+    got = o.decrypt_big(keys, small_engine.download(700, 16)).reshape(8, 2)
+    assert np.array_equal(got[:, 0], flags.all(axis=1).astype(np.int64))
+    assert np.array_equal(got[:, 1], flags.any(axis=1).astype(np.int64))
     small_engine.set_br_mode(0)
 
 
@@ -271,7 +309,11 @@ def test_full_parameters_4096_blocks(full_engine, full_oracle):
     # parameter set needs is var_pbs * 25 (max noise level 5) << var_ks + var_modswitch = 4.75e-6, i.e.
     # var_pbs << 1.9e-7; we hold the kernel to 1e-9 so that an accuracy regression is caught early.
     _record("pbs_output_noise", dict(kernel=1, blocks=B, variance=float(np.var(err)), max_abs=float(np.abs(err).max())))
-    assert np.var(err) <= 1.0e-9, np.var(err)
+    # Bound: 1.25 x the variance the CPU f64 route shows at these parameters (6.6e-10 on 384 samples, tests/
+    # test_oracle_tfhe.py::test_full_parameter_pbs_noise_budget; analytic decomposition floor 4.5e-10) = 8.25e-10.
+    # Measured on B200, 4096 samples: 6.7e-10 (profiles/r2_k3_accuracy.md).  What the parameter set NEEDS is far
+    # looser (var_pbs * 34 << var_ks + var_modswitch = 4.75e-6), so this bound catches an accuracy regression early.
+    assert np.var(err) <= 8.25e-10, np.var(err)
     assert np.abs(err).max() < 1.0 / 64
     # size-independent property: PBS with the identity LUT is idempotent on the decrypted value
     jobs2 = single_term_jobs(np.arange(B), B + np.arange(B), ident)
@@ -301,7 +343,8 @@ def test_full_parameters_latency_kernel(full_engine, full_oracle):
         assert np.array_equal(o.decrypt_big(keys, out), want), mode
         err = (o.phases(keys.s_glwe, out).astype(np.int64) - (want.astype(np.int64) << 59)).astype(float) / 2.0**64
         _record("pbs_output_noise", dict(kernel=mode, blocks=B, variance=float(np.var(err)), max_abs=float(np.abs(err).max())))
-        assert np.var(err) <= 1.0e-9, (mode, np.var(err))
+        # 280 samples: the 4096-sample bound (8.25e-10) widened by three standard errors of a sample variance
+        assert np.var(err) <= 8.25e-10 * (1 + 3 * np.sqrt(2.0 / B)), (mode, np.var(err))
     # 280 <= 2 x SMs: mode 0 picked the latency kernel -> the very same words as mode 2
     assert np.array_equal(outs[0], outs[2])
     # both kernels are valid PBS of the same input: phases differ by the scheme's own rounding noise only

@@ -134,3 +134,37 @@ def test_fft_external_product_close_to_exact(small_oracle):
     got = o.external_product_fft(o.fourier_bsk(keys)[: 4 * 2048], glwe, acc)
     d = (got - want).astype(np.int64).astype(float)
     assert np.sqrt(np.mean(d * d)) < 2.0**40  # 2^-24 of the torus
+
+
+def test_half_step_table_is_a_threshold(small_oracle):
+    """a table whose entries are 0x80 | e stands for e - 1/2 and the PBS result gets 1/2 added back
+    (include/fhestr_engine.h, fhestr_lut_register): f(v) = e[v] below 16 and 1 - e[v - 16] on the padding-bit half.
+    With e = 0 that is [v >= 16] -- AND / OR over 16 flags as ONE PBS on sum + constant"""
+    o, keys = small_oracle
+    table = [0x80] * 16
+    lut, post = o.lut_poly(table), o.lut_post(table)
+    assert post == 1 << 58 and o.lut_post(list(range(16))) == 0
+    with np.errstate(over="ignore"):
+        assert set(int(x) for x in np.unique(lut)) == {(1 << 58), (1 << 64) - (1 << 58)}
+    vals = np.arange(32)
+    cts = o.encrypt_big(keys, vals, seed=6)
+    for out in (o.pbs_exact(keys, lut[None], [0] * 32, cts, post=[post]),
+                o.pbs_fft(keys, o.fourier_bsk(keys), lut[None], [0] * 32, cts, post=[post])[0]):
+        assert np.array_equal(o.decrypt_big(keys, out), (vals >= 16).astype(np.int64))
+    # general e: f(v) = e[v], 1 - e[v - 16]
+    e = [(3 * x) % 5 % 2 for x in range(16)]
+    t2 = [0x80 | x for x in e]
+    out = o.pbs_exact(keys, o.lut_poly(t2)[None], [0] * 32, cts, post=[o.lut_post(t2)])
+    assert np.array_equal(o.decrypt_big(keys, out), np.array(e + [1 - x for x in e]))
+
+
+def test_decompose1_poly_equals_the_generic_decomposer(small_oracle):
+    import ctypes as C
+    o, _ = small_oracle
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 2**64, 4096, dtype=np.uint64)
+    x[:4] = [0, (1 << 63), (1 << 63) - (1 << 40), (1 << 64) - 1]
+    out = np.zeros(4096, np.int64)
+    o.lib.orc_decompose1_poly(x.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int(23), C.c_int(4096), out.ctypes.data_as(C.POINTER(C.c_int64)))
+    want = np.array([o.decompose(int(v), 23, 1)[0] for v in x])
+    assert np.array_equal(out, want)

@@ -25,6 +25,7 @@ def execute(o, keys, fbsk, graph, in_slots, in_vals, seed=7):
     info = graph.info
     jobs, off, npbs, first = graph.program()
     luts = np.stack([o.lut_poly(t) for t in graph.luts()]) if len(graph.luts()) else np.zeros((1, o.N), np.uint64)
+    posts = [o.lut_post(t) for t in graph.luts()] if len(graph.luts()) else [0]
     arena = np.zeros((info.slots_used, o.big), np.uint64)
     arena[np.asarray(in_slots, np.int64)] = o.encrypt_big(keys, in_vals, seed=seed)
     tslots, tvals = graph.trivials()
@@ -56,7 +57,7 @@ def execute(o, keys, fbsk, graph, in_slots, in_vals, seed=7):
                 if err >= 1 << 63:
                     err -= 1 << 64
                 worst = max(worst, abs(err) / delta)
-            out, _ = o.pbs_fft(keys, fbsk, luts, [int(j["lut"]) for j in jobs[a:a + n]], lin)
+            out, _ = o.pbs_fft(keys, fbsk, luts, [int(j["lut"]) for j in jobs[a:a + n]], lin, post=posts)
             for k, j in enumerate(jobs[a:a + n]):
                 arena[int(j["dst"])] = out[k]
         for j in jobs[a + n:b]:
