@@ -241,6 +241,7 @@ def query_leg(ctx, name, method, vals, steps):
     prog = g.bind(eng)
     res_slots = g.char_slots(out_ids).reshape(-1).astype(np.int64)
     contiguous = bool((np.diff(res_slots) == 1).all())
+    slots_u32 = np.ascontiguousarray(res_slots, np.uint32)
     host_res = torch.zeros((len(res_slots), eng.big), dtype=torch.int64).pin_memory()
 
     def download():
@@ -248,9 +249,8 @@ def query_leg(ctx, name, method, vals, steps):
             eng._ck(eng.lib.fhestr_ct_download(eng.h, C.c_uint32(int(res_slots[0])), C.c_uint32(len(res_slots)),
                                                C.cast(host_res.data_ptr(), C.POINTER(C.c_uint64))))
         else:
-            for i, sl in enumerate(res_slots):
-                eng._ck(eng.lib.fhestr_ct_download(eng.h, C.c_uint32(int(sl)), C.c_uint32(1),
-                                                   C.cast(host_res[i].data_ptr(), C.POINTER(C.c_uint64))))
+            eng._ck(eng.lib.fhestr_ct_download_slots(eng.h, slots_u32.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(len(res_slots)),
+                                                     C.cast(host_res.data_ptr(), C.POINTER(C.c_uint64))))
 
     reps = max(3, min(steps, 5)) if info.n_pbs < 50_000 else 3
     for _ in range(2 if info.n_pbs < 50_000 else 1):

@@ -65,6 +65,21 @@ int launch_trivial(u64* arena, uint32_t first, uint32_t count, const uint8_t* va
     return 1;
 }
 
+// ---- scattered arena blocks -> one contiguous staging buffer (fhestr_ct_download_slots: the result chars of a string
+// method are wherever their last level left them).  16 KiB per block, coalesced 16-byte... 8-byte words.
+__global__ void gather_blocks_kernel(const u64* arena, const uint32_t* slots, uint32_t count, u64* out) {
+    const uint32_t b = blockIdx.x;
+    if (b >= count) return;
+    const u64* src = arena + (size_t)slots[b] * (kN + 1);
+    u64* dst = out + (size_t)b * (kN + 1);
+    for (int i = threadIdx.x; i <= kN; i += blockDim.x) dst[i] = src[i];
+}
+int launch_gather_blocks(const u64* arena, const uint32_t* slots_dev, uint32_t count, u64* out, cudaStream_t s) {
+    if (!count) return 0;
+    gather_blocks_kernel<<<count, 256, 0, s>>>(arena, slots_dev, count, out);
+    return 1;
+}
+
 // ---- cross-GPU level barrier over NVLink peer memory (one process per GPU, arenas and flag arrays mapped with
 // cudaIpc).  The blind rotation of a level has already stored its results into every peer's arena; this only
 // orders those stores before the next level anywhere reads them.

@@ -48,6 +48,8 @@ struct fhestr_engine {
     size_t ks_cap = 0;
     uint8_t* d_bytes = nullptr;
     size_t bytes_cap = 0;
+    u64* gather_buf = nullptr;         // staging for fhestr_ct_download_slots
+    size_t gather_cap = 0;
     int br_mode = 0;                   // 0 = by level size, 1 = throughput kernel only, 2 = latency kernel only
     int wide_max_jobs = 0;             // levels of at most this many PBS jobs run on the latency kernel (0 = 2 x SMs)
     uint64_t launches = 0;
@@ -264,7 +266,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (e->own_arena && e->arena) cudaFree(e->arena);
     cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
     cudaFree(e->bsk_w); cudaFree(e->wide_tab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
-    cudaFree(e->luts); cudaFree(e->lut_post); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
+    cudaFree(e->gather_buf); cudaFree(e->luts); cudaFree(e->lut_post); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -375,6 +377,27 @@ int fhestr_ct_download(fhestr_engine* e, uint32_t first, uint32_t count, uint64_
     if ((uint64_t)first + count > e->arena_blocks) return fail(e, FHESTR_E_STATE, "download outside the arena");
     CK(cudaMemcpyAsync(host, e->arena + (size_t)first * (kN + 1), (size_t)count * (kN + 1) * sizeof(u64),
                        cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return check_peer_status(e);
+}
+
+int fhestr_ct_download_slots(fhestr_engine* e, const uint32_t* slots, uint32_t count, uint64_t* host) {
+    if (!e || !slots || !host) return FHESTR_E_INVALID;
+    if (!count) return FHESTR_OK;
+    for (uint32_t i = 0; i < count; i++)
+        if (slots[i] >= e->arena_blocks) return fail(e, FHESTR_E_STATE, "download outside the arena");
+    CK(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)count * (kN + 1) * sizeof(u64);
+    if (bytes > e->gather_cap) {
+        if (e->gather_buf) { CK(cudaFree(e->gather_buf)); e->gather_buf = nullptr; e->gather_cap = 0; }
+        CK(cudaMalloc(&e->gather_buf, bytes * 2));
+        e->gather_cap = bytes * 2;
+    }
+    int rc = stage_bytes(e, reinterpret_cast<const uint8_t*>(slots), (size_t)count * sizeof(uint32_t));
+    if (rc) return rc;
+    e->launches += launch_gather_blocks(e->arena, reinterpret_cast<const uint32_t*>(e->d_bytes), count, e->gather_buf, e->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, e->gather_buf, bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return check_peer_status(e);
 }

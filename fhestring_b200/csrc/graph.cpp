@@ -25,6 +25,8 @@ int Graph::lut_id(const std::array<uint8_t, 16>& t) {
 BlockId Graph::trivial_block(int value) {
     value = mod32(value);
     if (!triv_cache_init) {
+        nodes.reserve(1 << 16);
+        cse.reserve(1 << 16);
         for (int v = 0; v < 32; v++) {
             BlockNode n;
             n.kind = BKind::Trivial;
@@ -52,27 +54,34 @@ BlockId Graph::input_block() {
     return (BlockId)nodes.size() - 1;
 }
 
+static inline uint32_t rotl32(uint32_t x, int k) { k &= 31; return k ? (x << k) | (x >> (32 - k)) : x; }
+
+// set of values sum_i coeff_i * v_i + cst (mod 32) over v_i in vset_i: adding coeff * v shifts the whole partial set
+// by coeff * v, i.e. rotates its 32-bit mask
 uint32_t Graph::vset_of(const std::vector<std::pair<BlockId, int>>& ops, int cst) const {
     uint32_t S = 1u << mod32(cst);
     for (auto& op : ops) {
-        const uint32_t V = nodes[op.first].vset;
-        uint32_t T = 0;
-        for (int s = 0; s < 32; s++) {
-            if (!(S >> s & 1)) continue;
-            for (int v = 0; v < 32; v++) {
-                if (!(V >> v & 1)) continue;
-                const int sv = v >= 16 ? v - 32 : v;  // bit 4 set = negative value (padding bit)
-                T |= 1u << mod32(s + op.second * sv);
-            }
+        uint32_t V = nodes[op.first].vset, T = 0;
+        while (V) {
+            const int v = __builtin_ctz(V);
+            V &= V - 1;
+            const int sv = v >= 16 ? v - 32 : v;  // bit 4 set = negative value (padding bit)
+            T |= rotl32(S, mod32(op.second * sv));
         }
         S = T;
+        if (S == 0xFFFFFFFFu) break;
     }
     return S;
 }
 
 void Graph::flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, std::vector<Term>& terms, int& out_cst) {
     for (;;) {
-        std::map<BlockId, int> acc;
+        std::vector<std::pair<BlockId, int>>& acc = flat_scratch;
+        acc.clear();
+        auto add = [&](BlockId b, int k) {
+            for (auto& kv : acc) if (kv.first == b) { kv.second += k; return; }
+            acc.push_back({b, k});
+        };
         int c = cst;
         BlockId widest = 0;
         size_t widest_n = 0;
@@ -82,13 +91,14 @@ void Graph::flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, st
                 const int v = n.cst >= 16 ? n.cst - 32 : n.cst;
                 c += op.second * v;
             } else if (n.kind == BKind::Linear && !n.materialized) {
-                for (auto& t : n.terms) acc[t.blk] += op.second * t.coeff;
+                for (auto& t : n.terms) add(t.blk, op.second * t.coeff);
                 c += op.second * n.cst;
                 if (n.terms.size() > widest_n) { widest_n = n.terms.size(); widest = op.first; }
             } else {
-                acc[op.first] += op.second;
+                add(op.first, op.second);
             }
         }
+        std::sort(acc.begin(), acc.end());     // the CSE key is order-sensitive: canonical order by block id
         terms.clear();
         for (auto& kv : acc) if (kv.second != 0) terms.push_back(Term{kv.first, kv.second});
         out_cst = mod32(c);

@@ -152,6 +152,7 @@ private:
     uint32_t next_slot = 0;
     uint32_t n_input_nodes = 0;
     std::vector<BlockId> pending;  // nodes given a slot by the last compile()
+    std::vector<std::pair<BlockId, int>> flat_scratch;   // flatten(): merged (block, coefficient) pairs
 
     int lut_id(const std::array<uint8_t, 16>& t);
     void flatten(const std::vector<std::pair<BlockId, int>>& ops, int cst, std::vector<Term>& terms, int& out_cst);

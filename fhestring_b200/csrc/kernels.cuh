@@ -69,6 +69,8 @@ int launch_lut_poly(const uint8_t* table_dev, int entries, int delta_log, u64* o
 int launch_bsk_convert(const u64* bsk_std, int n, const cplx* tf, cplx* out, cudaStream_t s);
 int launch_ksk_correction(const u64* ksk, int rows /* N*L */, int n, int base_log, u64* corr, cudaStream_t s);
 int launch_trivial(u64* arena, uint32_t first, uint32_t count, const uint8_t* values_dev, int delta_log, cudaStream_t s);
+// arena[slots[b]] -> out[b], b < count
+int launch_gather_blocks(const u64* arena, const uint32_t* slots_dev, uint32_t count, u64* out, cudaStream_t s);
 // DFMA microbenchmark; returns total FMA count issued through *fmas
 int launch_dfma_peak(double* sink, int iters, unsigned long long* fmas, cudaStream_t s);
 

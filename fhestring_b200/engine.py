@@ -250,6 +250,14 @@ class Engine:
         self._ck(self.lib.fhestr_ct_download(self.h, C.c_uint32(first_block), C.c_uint32(count), _u64p(out)))
         return out
 
+    def download_slots(self, slots) -> np.ndarray:
+        """arena blocks named one by one -> [len(slots)][N+1]: gathered on the device, one copy"""
+        s = np.ascontiguousarray(slots, np.uint32).ravel()
+        out = np.zeros((len(s), self.big), np.uint64)
+        if len(s):
+            self._ck(self.lib.fhestr_ct_download_slots(self.h, s.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(len(s)), _u64p(out)))
+        return out
+
     def trivial(self, first_block: int, values):
         v = np.ascontiguousarray(values, np.uint8)
         self._ck(self.lib.fhestr_ct_trivial(self.h, C.c_uint32(first_block), C.c_uint32(len(v)),

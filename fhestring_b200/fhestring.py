@@ -267,14 +267,12 @@ class MyServerKey:
     def _download(self, chars) -> np.ndarray:
         self.flush(chars)
         slots = self.graph.char_slots(np.array([c.id for c in chars], np.uint32))
-        out = np.zeros((len(chars), 4, self.engine.big), np.uint64)
         flat = slots.reshape(-1).astype(np.int64)
         if len(flat) and (np.diff(flat) == 1).all():
-            out[:] = self.engine.download(int(flat[0]), len(flat)).reshape(out.shape)
+            out = self.engine.download(int(flat[0]), len(flat))
         else:
-            for i, s in enumerate(flat):
-                out.reshape(-1, self.engine.big)[i] = self.engine.download(int(s), 1)[0]
-        return out
+            out = self.engine.download_slots(flat)      # gathered on the device, one copy
+        return out.reshape(len(chars), 4, self.engine.big)
 
     def _ids(self, a):
         """char ids of one argument: an FheString, a list of FheAsciiChar (unpadded pattern) or a single char"""

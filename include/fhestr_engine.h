@@ -94,6 +94,9 @@ int fhestr_lut_download(fhestr_engine* e, int32_t lut_id, uint64_t* out_poly /* 
  * one must stay valid until the next synchronising call (fhestr_sync, fhestr_ct_download) */
 int fhestr_ct_upload(fhestr_engine* e, uint32_t first_block, uint32_t count, const uint64_t* host);
 int fhestr_ct_download(fhestr_engine* e, uint32_t first_block, uint32_t count, uint64_t* host);
+/* blocks named one by one (the chars of a result string sit wherever their last level left them): gathered on the
+ * device, ONE copy to the host */
+int fhestr_ct_download_slots(fhestr_engine* e, const uint32_t* slots, uint32_t count, uint64_t* host);
 /* the same without the synchronisation: `pinned_host` must be page-locked and stay valid until the next synchronising
  * call on the stream the copy was issued on (lets a caller overlap the copy-out of batch i with the PBS of batch i+1
  * by switching streams with fhestr_set_stream and ordering them with its own events) */

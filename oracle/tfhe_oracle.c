@@ -682,6 +682,17 @@ CLONES static void cmul_acc2(const double *restrict dr, const double *restrict d
         o1i[j] += dr[j] * g1[j + M] + di[j] * g1[j];
     }
 }
+/* A/B switch for the engine's design choice of keeping the blind-rotation accumulator on the 32-bit torus
+ * (fhestring_b200/csrc/br_core.cuh: acc_t): when set, the f64 route rounds the accumulator to the top 32 bits
+ * after the initial rotation and after every external product, exactly where the kernels do.  Everything else
+ * (FFT, decomposition, key) is shared, so the difference in output noise isolates that choice
+ * (tests/test_oracle_tfhe.py::test_accumulator_32_bit_ab, profiles/r2_k3_accuracy.md). */
+static int g_acc32 = 0;
+void orc_set_acc32(int on) { g_acc32 = on; }
+static void round_acc32(u64 *acc, int n) {
+    for (int j = 0; j < n; j++) acc[j] = (acc[j] + ((u64)1 << 31)) & ~(((u64)1 << 32) - 1);
+}
+
 /* FFT external product on one GGSW: acc[2][N] += ggsw_f (x) glwe[2][N].  scratch: 8*M doubles + N i64 */
 static void external_product_fft(const orc_params *p, const fft_plan *pl, const double *gf, const u64 *glwe,
                                  u64 *acc, double *scratch, i64 *dig) {
@@ -705,6 +716,7 @@ static void external_product_fft(const orc_params *p, const fft_plan *pl, const 
         }
     inv_add_torus(pl, o0r, o0i, acc, tsc);
     inv_add_torus(pl, o1r, o1i, acc + N, tsc);
+    if (g_acc32) round_acc32(acc, 2 * N);
 }
 void orc_external_product_fft(const orc_params *p, const double *ggsw_f, const u64 *glwe, u64 *acc) {
     fft_plan *pl = orc_fft_plan_new(p->N);
@@ -785,6 +797,7 @@ int orc_pbs_fft_batch(const orc_params *p, const double *fbsk, const u64 *ksk, c
                 const u32 bt = modswitch(ks[(size_t)q * (n + 1) + n], lg) % (2 * N);
                 memset(a, 0, sizeof(u64) * N);
                 monomial_mul(a + N, luts + (size_t)lut_ids[b0 + q] * N, (2 * N - bt) % (2 * N), N);
+                if (g_acc32) round_acc32(a, 2 * N);
             }
             for (int i = 0; i < n; i++)
                 for (int q = 0; q < gc; q++) {

@@ -86,6 +86,10 @@ class Oracle:
     def max_threads(self) -> int:
         return int(self.lib.orc_max_threads())
 
+    def set_acc32(self, on: bool):
+        """A/B switch: round the f64 route's accumulator to the 32-bit torus where the GPU kernels do (tfhe_oracle.c)"""
+        self.lib.orc_set_acc32(C.c_int(1 if on else 0))
+
     def set_threads(self, n: int) -> int:
         """OpenMP thread count for the batch entry points (torchrun exports OMP_NUM_THREADS=1); returns the count in effect"""
         return int(self.lib.orc_set_threads(C.c_int(int(n))))
