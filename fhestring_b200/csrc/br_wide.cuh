@@ -147,6 +147,7 @@ FHE_HD void wide_forward(Ctx& c, double (&re)[P][8], double (&im)[P][8], const W
 #pragma unroll
     for (int p = 0; p < P; p++) w_eval8_fwd(re[p], im[p], K.tw2);
     cplx* b1 = c.buf1();
+    c.pre_write_sync();   // single-buffer contexts: every thread has read exchange 1 before anyone overwrites it
     {
         const int base = (t >> 4) * 8 * 17 + (t & 15);
 #pragma unroll
@@ -179,6 +180,7 @@ FHE_HD void wide_inverse(Ctx& c, double (&re)[P][8], double (&im)[P][8], const W
 #pragma unroll
     for (int p = 0; p < P; p++) w_eval8_inv(re[p], im[p], K.tw3);
     cplx* b0 = c.buf0();
+    c.pre_write_sync();
     {
         const int base = (t >> 1) * 18 + (t & 1) * 9;
 #pragma unroll
@@ -203,6 +205,7 @@ FHE_HD void wide_inverse(Ctx& c, double (&re)[P][8], double (&im)[P][8], const W
 #pragma unroll
     for (int p = 0; p < P; p++) w_eval8_inv(re[p], im[p], K.tw2);
     cplx* b1 = c.buf1();
+    c.pre_write_sync();
     {
         const int base = (t >> 4) * 128 + (t & 15);
 #pragma unroll
@@ -256,6 +259,7 @@ FHE_HD void wide_cmux_step(Ctx& c, acc_t (&a)[2][16], int e, int step, const Wid
         re[1][u] = fma(d1r, g11.x, fma(-d1i, g11.y, fma(d0r, g01.x, -(d0i * g01.y))));
         im[1][u] = fma(d1r, g11.y, fma(d1i, g11.x, fma(d0r, g01.y, d0i * g01.x)));
     }
+    c.key_release(step);   // shared-tile contexts: this thread is done with the step's key tile
     wide_inverse<2>(c, re, im, K);
 #pragma unroll
     for (int p = 0; p < 2; p++) {
@@ -316,7 +320,8 @@ FHE_HD void wide_thread_main(Ctx& c, const BrJobView& job, const WideConsts& K) 
     }
     c.sync();
     for (int i = 0; i < n; i++) {
-        if (i + 1 < n) c.key_prefetch(i + 1);
+        if (i + 1 < n) c.key_prefetch(i + 1);   // ring contexts: next step's tile
+        c.key_prefetch_current(i);              // single-tile contexts: this step's tile (everyone is done with the last)
         // e == 0 is NOT skipped here (the key pipeline stays in step): every digit is exactly 0, so is the product
         wide_cmux_step(c, a, at[i], i, K);
     }

@@ -51,7 +51,8 @@ struct fhestr_engine {
     u64* gather_buf = nullptr;         // staging for fhestr_ct_download_slots
     size_t gather_cap = 0;
     int br_mode = 0;                   // 0 = by level size, 1 = throughput kernel only, 2 = latency kernel only
-    int wide_max_jobs = 0;             // levels of at most this many PBS jobs run on the latency kernel (0 = 2 x SMs)
+    int wide_max_jobs = 0;             // levels of at most this many PBS jobs run on the latency kernel (0 = 3 x SMs)
+    int wide_shape = 0;                // 0 = by level size, 1 = one PBS per SM, 2 = the pair form (two PBS per SM)
     uint64_t launches = 0;
     bool timing = false;
     struct Timed { cudaEvent_t a, b, c; uint32_t pbs; };   // a..b keyswitch, b..c blind rotation
@@ -427,8 +428,15 @@ int fhestr_ct_trivial(fhestr_engine* e, uint32_t first, uint32_t count, const ui
 static bool use_wide(const fhestr_engine* e, uint32_t n_pbs) {
     if (e->br_mode == 1) return false;
     if (e->br_mode == 2) return true;
-    const uint32_t lim = e->wide_max_jobs > 0 ? (uint32_t)e->wide_max_jobs : 2u * (uint32_t)e->n_sms;
+    const uint32_t lim = e->wide_max_jobs > 0 ? (uint32_t)e->wide_max_jobs : 3u * (uint32_t)e->n_sms;
     return n_pbs <= lim;
+}
+
+// the latency kernel's two forms: ONE PBS per SM (128 threads, two-tile key ring) for levels of at most one job per SM,
+// TWO PBS per SM (256 threads, one shared key tile) up to wide_max_jobs
+static int launch_wide(const fhestr_engine* e, const BrBatchArgs& br, uint32_t n_pbs) {
+    const bool pair = e->wide_shape == 2 || (e->wide_shape == 0 && n_pbs > (uint32_t)e->n_sms);
+    return pair ? launch_blind_rotate_wide2(br, e->stream) : launch_blind_rotate_wide(br, e->stream);
 }
 
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
@@ -452,7 +460,7 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         if (e->peers_attached && peer_stores) {
             for (uint32_t r = 0; r < e->world; r++) if (r != e->rank) br.peer_arena[br.n_peers++] = e->peer_arena[r];
         }
-        e->launches += use_wide(e, n_pbs) ? launch_blind_rotate_wide(br, e->stream) : launch_blind_rotate(br, e->stream);
+        e->launches += use_wide(e, n_pbs) ? launch_wide(e, br, n_pbs) : launch_blind_rotate(br, e->stream);
         if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
@@ -744,7 +752,7 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
     br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.init_acc = d_init; br.out_acc = d_out;
     br.n = e->prm.n; br.B = (int)count;
     br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
-    e->launches += use_wide(e, count) ? launch_blind_rotate_wide(br, e->stream) : launch_blind_rotate(br, e->stream);
+    e->launches += use_wide(e, count) ? launch_wide(e, br, count) : launch_blind_rotate(br, e->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc_out_host, d_out, acc_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -824,8 +832,9 @@ int fhestr_set_keyswitch_path(fhestr_engine* e, int path) {
 }
 
 int fhestr_set_br_mode(fhestr_engine* e, int mode, int wide_max_jobs) {
-    if (!e || mode < 0 || mode > 2 || wide_max_jobs < 0) return FHESTR_E_INVALID;
-    e->br_mode = mode;
+    if (!e || mode < 0 || mode > 4 || wide_max_jobs < 0) return FHESTR_E_INVALID;
+    e->br_mode = mode > 2 ? 2 : mode;
+    e->wide_shape = mode > 2 ? mode - 2 : 0;     // 3 / 4: the latency kernel forced to its single / pair form
     e->wide_max_jobs = wide_max_jobs;
     return FHESTR_OK;
 }

@@ -49,6 +49,8 @@ int launch_blind_rotate(const BrBatchArgs& a, cudaStream_t s);
 cudaError_t blind_rotate_configure();
 // the same in its latency form: one PBS per 128-thread CTA, one CTA per SM, key tiles by bulk TMA (br_wide.cuh)
 int launch_blind_rotate_wide(const BrBatchArgs& a, cudaStream_t s);
+// pair form: two PBS per 256-thread CTA sharing one TMA-fed key tile per step
+int launch_blind_rotate_wide2(const BrBatchArgs& a, cudaStream_t s);
 cudaError_t blind_rotate_wide_configure();
 int launch_bsk_convert_wide(const u64* bsk_std, int n, const WideConsts* tab, cplx* out, cudaStream_t s);
 cudaError_t keyswitch_configure();  // opt in to the large dynamic shared memory carve-out

@@ -240,10 +240,12 @@ int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_
 /* number of kernels this engine has launched so far (bench.py's gpu_launches) */
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
 /* Which blind-rotation kernel runs a level.  mode 0 (default): by level size -- levels of at most wide_max_jobs PBS
- * jobs (0 = twice the SM count) run on the latency kernel (one PBS per SM over 128 threads, key tiles by bulk TMA),
- * larger ones on the throughput kernel (four PBS per SM).  mode 1 / 2 force the throughput / latency kernel (tests,
- * measurements).  Both kernels compute the same function; their outputs are different valid ciphertexts of the same
- * plaintext (two f64 FFT orders), see DESIGN.md. */
+ * jobs (0 = three times the SM count) run on the latency kernel, larger ones on the throughput kernel (four PBS per
+ * SM, one pair of warps each).  The latency kernel has two forms, also picked by size: ONE PBS per SM over 128 threads
+ * with a two-tile key ring fed by bulk TMA (up to one job per SM), and TWO PBS per SM over 256 threads sharing one
+ * key tile (above).  mode 1 forces the throughput kernel, 2 the latency kernel (form by size), 3 / 4 its single /
+ * pair form (tests, measurements).  All kernels compute the same function; their outputs are different valid
+ * ciphertexts of the same plaintext (different f64 FFT orders), see DESIGN.md. */
 int fhestr_set_br_mode(fhestr_engine* e, int mode, int wide_max_jobs);
 /* keyswitch implementation: 0 = tensor cores (u8 limb-split IMMA GEMM, default), 1 = CUDA cores (u64 IMAD);
  * both are exact and produce identical words */

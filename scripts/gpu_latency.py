@@ -26,11 +26,11 @@ vals = np.random.default_rng(0).integers(0, 16, BMAX).astype(np.uint8)
 eng.upload(0, ck.encrypt_blocks(vals))
 ident = eng.lut(list(range(16)))
 rows = []
-for B in ([int(x) for x in sys.argv[1:]] or (1, 2, 16, 32, 74, 148, 149, 250, 296, 297, 444, 500, 592, 1184)):
+for B in ([int(x) for x in sys.argv[1:]] or (1, 16, 148, 149, 250, 296, 297, 444, 500, 592, 1184)):
     jobs = single_term_jobs(BMAX + np.arange(B), np.arange(B), ident)
     prog = eng.program(jobs, [0, B])
     row = dict(jobs=B)
-    for mode, name in ((1, "throughput"), (2, "latency")):
+    for mode, name in ((1, "throughput"), (3, "latency_single"), (4, "latency_pair"), (0, "by_level_size")):
         eng.set_br_mode(mode)
         for _ in range(2):
             prog.run()

@@ -26,6 +26,9 @@ struct HostWideCtx {
     uint16_t* atilde() { return atilde_; }
     void sync() { bar->arrive_and_wait(); }
     void key_prefetch(int) {}
+    void key_prefetch_current(int) {}
+    void key_release(int) {}
+    void pre_write_sync() {}
     const cplx* key_wait(int step) { return bsk_ + (size_t)step * kWKeyTile; }
     acc_t acc_ld_rot(int p, uint32_t x) const {
         const acc_t v = acc_[p * kN + ((x >> 2) & (kN - 1))];

@@ -138,7 +138,7 @@ def test_keyswitch_tensor_core_and_cuda_core_paths_identical(full_engine, full_o
     assert np.array_equal(a[:len(lin)], o.keyswitch(keys, lin))
 
 
-@pytest.mark.parametrize("br_mode", [1, 2], ids=["throughput_kernel", "latency_kernel"])
+@pytest.mark.parametrize("br_mode", [1, 3, 4], ids=["throughput_kernel", "latency_kernel_single", "latency_kernel_pair"])
 def test_single_external_product_tolerance(build_lib, small_oracle, br_mode):
     """K3 on one CMUX step with a random (worst-case, full-range) GLWE, vs exact integers + golden; both kernels"""
     from fhestring_b200.engine import Engine
@@ -180,7 +180,8 @@ def test_single_external_product_tolerance(build_lib, small_oracle, br_mode):
     eng.close()
 
 
-@pytest.mark.parametrize("br_mode", [0, 1, 2], ids=["by_level_size", "throughput_kernel", "latency_kernel"])
+@pytest.mark.parametrize("br_mode", [0, 1, 2, 3, 4], ids=["by_level_size", "throughput_kernel", "latency_kernel",
+                                                           "latency_kernel_single", "latency_kernel_pair"])
 def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, br_mode):
     """K0..K4 end to end on 32 block values incl. the padding-bit half (negacyclic sign), several LUTs,
     batch size not a multiple of the CTA tile, both blind-rotation kernels"""
@@ -201,7 +202,7 @@ def test_pbs_small_all_values_and_padding_bit(small_engine, small_oracle, br_mod
     small_engine.set_br_mode(0)
 
 
-@pytest.mark.parametrize("br_mode", [1, 2], ids=["throughput_kernel", "latency_kernel"])
+@pytest.mark.parametrize("br_mode", [1, 3, 4], ids=["throughput_kernel", "latency_kernel_single", "latency_kernel_pair"])
 def test_half_step_table_threshold_and_or(small_engine, small_oracle, br_mode):
     """K5 + K4 for half-step tables (entries 0x80 | e = e - 1/2, the engine adds 1/2 back to the extracted body): the
     polynomial is bit-exact against the oracle, all 32 block values decrypt to [v >= 16], and an AND and an OR over 16
@@ -333,7 +334,7 @@ def test_full_parameters_latency_kernel(full_engine, full_oracle):
     table = [(7 * x + 2) % 16 for x in range(16)]
     jobs = single_term_jobs(4096 + np.arange(B), np.arange(B), full_engine.lut(table))
     outs = {}
-    for mode in (2, 1, 0):
+    for mode in (2, 1, 0, 3):
         full_engine.set_br_mode(mode)
         full_engine.pbs_batch(jobs)
         outs[mode] = full_engine.download(4096, B)
@@ -345,8 +346,10 @@ def test_full_parameters_latency_kernel(full_engine, full_oracle):
         _record("pbs_output_noise", dict(kernel=mode, blocks=B, variance=float(np.var(err)), max_abs=float(np.abs(err).max())))
         # 280 samples: the 4096-sample bound (8.25e-10) widened by three standard errors of a sample variance
         assert np.var(err) <= 8.25e-10 * (1 + 3 * np.sqrt(2.0 / B)), (mode, np.var(err))
-    # 280 <= 2 x SMs: mode 0 picked the latency kernel -> the very same words as mode 2
+    # 148 < 280 <= 3 x SMs: modes 0 and 2 pick the latency kernel's pair form -> the very same words; the single form
+    # runs the same arithmetic per PBS (one transform code, br_wide.cuh) -> the same words again
     assert np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[3], outs[2])
     # both kernels are valid PBS of the same input: phases differ by the scheme's own rounding noise only
     dp = (o.phases(keys.s_glwe, outs[1]) - o.phases(keys.s_glwe, outs[2])).astype(np.int64).astype(float) / 2.0**64
     assert np.abs(dp).max() < 2.0**-11

@@ -89,7 +89,7 @@ def test_engine_against_fixture(fx, build_lib):
         jobs = single_term_jobs(512 + np.arange(T), np.arange(T), 0)
         jobs["lut"] = [ids[int(l)] for l in fx.triple_lut]
         assert np.array_equal(eng.debug_keyswitch(jobs), fx.triple_ks)
-        for mode in (1, 2):
+        for mode in (1, 3, 4):
             eng.set_br_mode(mode)
             eng.pbs_batch(jobs)
             got = eng.download(512, T)
