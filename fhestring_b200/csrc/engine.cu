@@ -433,10 +433,25 @@ static bool use_wide(const fhestr_engine* e, uint32_t n_pbs) {
 }
 
 // the latency kernel's two forms: ONE PBS per SM (128 threads, two-tile key ring) for levels of at most one job per SM,
-// TWO PBS per SM (256 threads, one shared key tile) up to wide_max_jobs
+// TWO PBS per SM (256 threads, one shared key tile) up to two jobs per SM; a level between two and three jobs per SM
+// runs as one full wave of pairs followed by one wave of singles (3.55 + 2.14 ms against 6.0-6.8 ms on the
+// throughput kernel, profiles/r2_level_latency.md)
+static BrBatchArgs br_slice(const BrBatchArgs& br, uint32_t first, uint32_t count) {
+    BrBatchArgs s = br;
+    s.ks = br.ks + (size_t)first * (br.n + 1);
+    if (br.jobs) s.jobs = br.jobs + first;
+    if (br.lut_ids) s.lut_ids = br.lut_ids + first;
+    if (br.init_acc) s.init_acc = br.init_acc + (size_t)first * 2 * kN;
+    if (br.out_acc) s.out_acc = br.out_acc + (size_t)first * 2 * kN;
+    s.B = (int)count;
+    return s;
+}
 static int launch_wide(const fhestr_engine* e, const BrBatchArgs& br, uint32_t n_pbs) {
-    const bool pair = e->wide_shape == 2 || (e->wide_shape == 0 && n_pbs > (uint32_t)e->n_sms);
-    return pair ? launch_blind_rotate_wide2(br, e->stream) : launch_blind_rotate_wide(br, e->stream);
+    const uint32_t sms = (uint32_t)e->n_sms;
+    if (e->wide_shape == 1 || (e->wide_shape == 0 && n_pbs <= sms)) return launch_blind_rotate_wide(br, e->stream);
+    if (e->wide_shape == 2 || n_pbs <= 2 * sms) return launch_blind_rotate_wide2(br, e->stream);
+    return launch_blind_rotate_wide2(br_slice(br, 0, 2 * sms), e->stream) +
+           launch_blind_rotate_wide(br_slice(br, 2 * sms, n_pbs - 2 * sms), e->stream);
 }
 
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
