@@ -16,7 +16,8 @@ from fhestring_b200.engine import Engine, single_term_jobs  # noqa: E402
 
 ck = ClientKey(seed=1)
 bsk, ksk = ck.server_keys()
-BMAX = 1184
+SIZES = [int(x) for x in sys.argv[1:]] or [1, 16, 148, 149, 250, 296, 297, 444, 500, 592, 1184]
+BMAX = max(1184, max(SIZES))
 eng = Engine(arena_blocks=2 * BMAX + 8)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
@@ -26,7 +27,7 @@ vals = np.random.default_rng(0).integers(0, 16, BMAX).astype(np.uint8)
 eng.upload(0, ck.encrypt_blocks(vals))
 ident = eng.lut(list(range(16)))
 rows = []
-for B in ([int(x) for x in sys.argv[1:]] or (1, 16, 148, 149, 250, 296, 297, 444, 500, 592, 1184)):
+for B in SIZES:
     jobs = single_term_jobs(BMAX + np.arange(B), np.arange(B), ident)
     prog = eng.program(jobs, [0, B])
     row = dict(jobs=B)
