@@ -28,6 +28,8 @@ constexpr int kWSmemBytes = kWHeadBytes + kWPad + kWAccBytes + kWBuf0Bytes + kWB
 static_assert(kWSmemBytes <= 227 * 1024, "one CTA's shared memory");
 
 struct DevWideCtx {
+    static constexpr bool kPipelined = true;    // br_wide.cuh: wide_cmux_step_pipe, one named barrier per polynomial
+    __device__ __forceinline__ void sync_poly(int p) { asm volatile("bar.sync %0, 128;" ::"r"(p + 1) : "memory"); }
     int tid_;
     acc_t* acc_;
     uint32_t acc_s_;        // shared-space address of polynomial 0's accumulator, 8 KiB aligned (polynomial 1: + 8 KiB)
@@ -158,6 +160,7 @@ constexpr int kW2SmemBytes = kW2HeadBytes + 8192 + 2 * kW2PbsBytes + kWKeyBytes;
 static_assert(kW2SmemBytes <= 227 * 1024, "one CTA's shared memory");
 
 struct DevWide2Ctx {
+    static constexpr bool kPipelined = false;   // one exchange buffer per PBS: the plain step with its extra barriers
     int tid_, grp_, n_groups_;
     acc_t* acc_;
     uint32_t acc_s_;

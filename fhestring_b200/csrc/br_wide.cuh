@@ -275,6 +275,165 @@ FHE_HD void wide_cmux_step(Ctx& c, acc_t (&a)[2][16], int e, int step, const Wid
     c.sync();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same CMUX step as a two-stream software pipeline (contexts with one barrier PER POLYNOMIAL: c.sync_poly(p)).
+// The plain step above runs both polynomials through every exchange behind ONE barrier, so all four warps of a PBS are
+// always in the same phase and the shared-memory pipe and the FP64 pipe take turns (ncu: 57 % + 47 % of the step).
+// Here polynomial 1 runs half a phase behind polynomial 0: every batch of shared-memory stores is followed by an FP64
+// block of the OTHER polynomial before its barrier, and every batch of loads by one before its consumer, so the two
+// pipes overlap.  Same arithmetic, same order of operations per polynomial: bit-identical results.
+FHE_HD void w_eval8_fwd_ab(double (&re)[8], double (&im)[8], const cplx (&tw)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) w_bfly(re[k], im[k], re[k + 4], im[k + 4], tw[0].x, tw[0].y);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        w_bfly(re[k], im[k], re[k + 2], im[k + 2], tw[1].x, tw[1].y);
+        w_bfly(re[4 + k], im[4 + k], re[6 + k], im[6 + k], -tw[1].y, tw[1].x);
+    }
+}
+FHE_HD void w_eval8_fwd_c(double (&re)[8], double (&im)[8], const cplx (&tw)[4]) {
+    w_bfly(re[0], im[0], re[1], im[1], tw[2].x, tw[2].y);
+    w_bfly(re[2], im[2], re[3], im[3], -tw[2].y, tw[2].x);
+    w_bfly(re[4], im[4], re[5], im[5], tw[3].x, tw[3].y);
+    w_bfly(re[6], im[6], re[7], im[7], -tw[3].y, tw[3].x);
+}
+FHE_HD void w_eval8_inv_c(double (&re)[8], double (&im)[8], const cplx (&tw)[4]) {
+    w_ibfly(re[0], im[0], re[1], im[1], tw[2].x, tw[2].y);
+    w_ibfly(re[2], im[2], re[3], im[3], -tw[2].y, tw[2].x);
+    w_ibfly(re[4], im[4], re[5], im[5], tw[3].x, tw[3].y);
+    w_ibfly(re[6], im[6], re[7], im[7], -tw[3].y, tw[3].x);
+}
+FHE_HD void w_eval8_inv_ba(double (&re)[8], double (&im)[8], const cplx (&tw)[4]) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        w_ibfly(re[k], im[k], re[k + 2], im[k + 2], tw[1].x, tw[1].y);
+        w_ibfly(re[4 + k], im[4 + k], re[6 + k], im[6 + k], -tw[1].y, tw[1].x);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) w_ibfly(re[k], im[k], re[k + 4], im[k + 4], tw[0].x, tw[0].y);
+}
+
+template <class Ctx>
+FHE_HD void wide_cmux_step_pipe(Ctx& c, acc_t (&a)[2][16], int e, int step, const WideConsts& K) {
+    const int t = c.tid();
+    double re[2][8], im[2][8];
+    cplx tw1[4];
+    wide_tw1(tw1);
+    cplx* b0 = c.buf0();
+    cplx* b1 = c.buf1();
+    const uint32_t x0 = (uint32_t)((t - e) & (2 * kN - 1)) << 2;
+    const int i1 = (t >> 4) * 128 + (t & 15);            // exchange 1, reader side (and inverse exchange 1, writer side)
+    const int i2w = (t >> 4) * 8 * 17 + (t & 15);        // exchange 2, writer
+    const int i2r = (t >> 1) * 17;                       // exchange 2, reader
+    const int i3w = (t >> 1) * 18 + (t & 1) * 9;         // inverse exchange 2, writer
+    const int i3r = (t >> 4) * 8 * 18 + (t & 7);         // inverse exchange 2, reader
+
+#define W_GATHER(p)                                                                              \
+    _Pragma("unroll") for (int k = 0; k < 8; k++) {                                              \
+        re[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);                       \
+        im[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);           \
+    }
+#define W_S1(p) _Pragma("unroll") for (int j = 0; j < 8; j++) b0[p * kWX1 + j * 128 + t] = cplx{re[p][j], im[p][j]};
+#define W_L1(p) _Pragma("unroll") for (int m = 0; m < 8; m++) { const cplx v = b0[p * kWX1 + i1 + 16 * m]; re[p][m] = v.x; im[p][m] = v.y; }
+#define W_S2(p) _Pragma("unroll") for (int l = 0; l < 8; l++) b1[p * kWX2 + i2w + l * 17] = cplx{re[p][l], im[p][l]};
+#define W_L2(p)                                                                                  \
+    _Pragma("unroll") for (int k = 0; k < 8; k++) {                                              \
+        const cplx lo = b1[p * kWX2 + i2r + k];                                                  \
+        const cplx hi = b1[p * kWX2 + i2r + k + 8];                                              \
+        re[p][k] = fma(K.rg.x, hi.x, fma(-K.rg.y, hi.y, lo.x));                                  \
+        im[p][k] = fma(K.rg.x, hi.y, fma(K.rg.y, hi.x, lo.y));                                   \
+    }
+#define W_S3(p) _Pragma("unroll") for (int k = 0; k < 8; k++) b0[p * kWX2I + i3w + k] = cplx{re[p][k], im[p][k]};
+#define W_L3(p)                                                                                  \
+    _Pragma("unroll") for (int l = 0; l < 8; l++) {                                              \
+        const cplx lo = b0[p * kWX2I + i3r + l * 18];                                            \
+        const cplx hi = b0[p * kWX2I + i3r + l * 18 + 9];                                        \
+        const double dr = fma(K.sig, hi.x, lo.x), di = fma(K.sig, hi.y, lo.y);                   \
+        re[p][l] = fma(K.kap[l].x, dr, -(K.kap[l].y * di));                                      \
+        im[p][l] = fma(K.kap[l].x, di, K.kap[l].y * dr);                                         \
+    }
+#define W_S4(p) _Pragma("unroll") for (int m = 0; m < 8; m++) b1[p * kWX1 + i1 + 16 * m] = cplx{re[p][m], im[p][m]};
+#define W_L4(p) _Pragma("unroll") for (int j = 0; j < 8; j++) { const cplx v = b1[p * kWX1 + j * 128 + t]; re[p][j] = v.x; im[p][j] = v.y; }
+#define W_ACC(p)                                                                                 \
+    {                                                                                            \
+        acc_t* acc = c.acc(p);                                                                   \
+        _Pragma("unroll") for (int k = 0; k < 8; k++) {                                          \
+            a[p][k] += torus32_conv(re[p][k], k);                                                \
+            a[p][8 + k] += torus32_conv(im[p][k], k);                                            \
+            acc[128 * k + t] = a[p][k];                                                          \
+            acc[128 * k + t + kM] = a[p][8 + k];                                                 \
+        }                                                                                        \
+    }
+
+    // ---- forward
+    c.sync_poly(0);                      // accumulator 0 of the previous step is complete
+    W_GATHER(0)
+    w_eval8_fwd(re[0], im[0], tw1);
+    W_S1(0)
+    c.sync_poly(1);
+    W_GATHER(1)
+    w_eval8_fwd_ab(re[1], im[1], tw1);
+    c.sync_poly(0); W_L1(0)
+    w_eval8_fwd_c(re[1], im[1], tw1);
+    W_S1(1)
+    w_eval8_fwd_ab(re[0], im[0], K.tw2);
+    c.sync_poly(1); W_L1(1)
+    w_eval8_fwd_c(re[0], im[0], K.tw2);
+    W_S2(0)
+    w_eval8_fwd_ab(re[1], im[1], K.tw2);
+    c.sync_poly(0); W_L2(0)
+    w_eval8_fwd_c(re[1], im[1], K.tw2);
+    W_S2(1)
+    w_eval8_fwd_ab(re[0], im[0], K.tw3);
+    c.sync_poly(1); W_L2(1)
+    w_eval8_fwd_c(re[0], im[0], K.tw3);
+    w_eval8_fwd(re[1], im[1], K.tw3);
+    // ---- GGSW product (both polynomials of every spectrum point are in this thread)
+    const cplx* key = c.key_wait(step);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const cplx g00 = key[wide_key_index(0, 0, u, t)], g01 = key[wide_key_index(0, 1, u, t)];
+        const cplx g10 = key[wide_key_index(1, 0, u, t)], g11 = key[wide_key_index(1, 1, u, t)];
+        const double d0r = re[0][u], d0i = im[0][u], d1r = re[1][u], d1i = im[1][u];
+        re[0][u] = fma(d1r, g10.x, fma(-d1i, g10.y, fma(d0r, g00.x, -(d0i * g00.y))));
+        im[0][u] = fma(d1r, g10.y, fma(d1i, g10.x, fma(d0r, g00.y, d0i * g00.x)));
+        re[1][u] = fma(d1r, g11.x, fma(-d1i, g11.y, fma(d0r, g01.x, -(d0i * g01.y))));
+        im[1][u] = fma(d1r, g11.y, fma(d1i, g11.x, fma(d0r, g01.y, d0i * g01.x)));
+    }
+    c.key_release(step);
+    // ---- inverse
+    w_eval8_inv(re[0], im[0], K.tw3);
+    W_S3(0)
+    w_eval8_inv_c(re[1], im[1], K.tw3);
+    c.sync_poly(0); W_L3(0)
+    w_eval8_inv_ba(re[1], im[1], K.tw3);
+    W_S3(1)
+    w_eval8_inv_c(re[0], im[0], K.tw2);
+    c.sync_poly(1); W_L3(1)
+    w_eval8_inv_ba(re[0], im[0], K.tw2);
+    W_S4(0)
+    w_eval8_inv_c(re[1], im[1], K.tw2);
+    c.sync_poly(0); W_L4(0)
+    w_eval8_inv_ba(re[1], im[1], K.tw2);
+    W_S4(1)
+    w_eval8_inv_c(re[0], im[0], tw1);
+    c.sync_poly(1); W_L4(1)
+    w_eval8_inv_ba(re[0], im[0], tw1);
+    W_ACC(0)
+    w_eval8_inv(re[1], im[1], tw1);
+    W_ACC(1)
+#undef W_GATHER
+#undef W_S1
+#undef W_L1
+#undef W_S2
+#undef W_L2
+#undef W_S3
+#undef W_L3
+#undef W_S4
+#undef W_L4
+#undef W_ACC
+}
+
 // Forward transform of one standard-domain GGSW polynomial into tile position (row, col) (key conversion, once)
 template <class Ctx>
 FHE_HD void wide_bsk_poly_forward(Ctx& c, const u64* poly, cplx* out_step, int row, int col, const WideConsts& K) {
@@ -323,8 +482,10 @@ FHE_HD void wide_thread_main(Ctx& c, const BrJobView& job, const WideConsts& K) 
         if (i + 1 < n) c.key_prefetch(i + 1);   // ring contexts: next step's tile
         c.key_prefetch_current(i);              // single-tile contexts: this step's tile (everyone is done with the last)
         // e == 0 is NOT skipped here (the key pipeline stays in step): every digit is exactly 0, so is the product
-        wide_cmux_step(c, a, at[i], i, K);
+        if constexpr (Ctx::kPipelined) wide_cmux_step_pipe(c, a, at[i], i, K);
+        else wide_cmux_step(c, a, at[i], i, K);
     }
+    if constexpr (Ctx::kPipelined) c.sync();   // the pipelined step leaves its last accumulator stores un-fenced
     if (job.out_acc) {
 #pragma unroll
         for (int p = 0; p < 2; p++)

@@ -11,7 +11,11 @@
 
 using namespace fhestr;
 
+#ifndef EMU_PIPELINED
+#define EMU_PIPELINED 0
+#endif
 struct HostWideCtx {
+    static constexpr bool kPipelined = EMU_PIPELINED != 0;
     int tid_;
     acc_t* acc_;            // [2][kN]
     cplx* buf0_;
@@ -19,6 +23,9 @@ struct HostWideCtx {
     uint16_t* atilde_;
     const cplx* bsk_;       // [n][kWKeyTile]
     std::barrier<>* bar;
+    std::barrier<>* pbar0 = nullptr;   // one barrier per polynomial (the pipelined step)
+    std::barrier<>* pbar1 = nullptr;
+    void sync_poly(int p) { (p ? pbar1 : pbar0)->arrive_and_wait(); }
     int tid() const { return tid_; }
     acc_t* acc(int p) { return acc_ + p * kN; }
     cplx* buf0() { return buf0_; }
@@ -64,12 +71,12 @@ void emu_wide_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init
     std::vector<acc_t> acc(2 * kN);
     std::vector<cplx> b0(kWBuf0), b1(kWBuf1);
     std::vector<uint16_t> at(n + 256);
-    std::barrier<> bar(kWT);
+    std::barrier<> bar(kWT), pb0(kWT), pb1(kWT);
     BrJobView job{ks, lut, init_acc, out_lwe, out_acc, n};
     std::vector<std::thread> th;
     for (int t = 0; t < kWT; t++)
         th.emplace_back([&, t] {
-            HostWideCtx c{t, acc.data(), b0.data(), b1.data(), at.data(), reinterpret_cast<const cplx*>(bsk_w), &bar};
+            HostWideCtx c{t, acc.data(), b0.data(), b1.data(), at.data(), reinterpret_cast<const cplx*>(bsk_w), &bar, &pb0, &pb1};
             wide_thread_main(c, job, tab[t]);
         });
     for (auto& t : th) t.join();

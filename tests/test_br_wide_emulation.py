@@ -12,15 +12,18 @@ import pytest
 from conftest import ROOT, monomial_mul
 
 
-@pytest.fixture(scope="module")
-def emu():
+# both forms of the CMUX step: the plain one (one barrier for both polynomials: the pair kernel) and the two-stream
+# software pipeline with one barrier per polynomial (the single kernel)
+@pytest.fixture(scope="module", params=[0, 1], ids=["plain_step", "pipelined_step"])
+def emu(request):
     src = os.path.join(ROOT, "tests", "emu", "br_wide_emu.cpp")
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libbr_wide_emu.so")
+    lib = os.path.join(out_dir, f"libbr_wide_emu_{request.param}.so")
     deps = [src] + [os.path.join(ROOT, "fhestring_b200", "csrc", f) for f in ("br_wide.cuh", "br_core.cuh", "fft32_gen.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", lib, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", f"-DEMU_PIPELINED={request.param}",
+                               "-o", lib, src])
     return C.CDLL(lib)
 
 
@@ -84,3 +87,22 @@ def test_small_pbs_decrypts(emu):
     for b in range(len(vals)):
         emu.emu_wide_blind_rotate(n, _p(ks[b]), _p(lut), None, _p(bskw, C.c_double), _p(outs[b]), None)
     assert np.array_equal(o3.decrypt_big(k3, outs), np.array([table[v] for v in vals]))
+
+
+def test_pipelined_step_is_bit_identical_to_the_plain_step(small_oracle):
+    """same arithmetic in the same order per polynomial: the two forms of the step must produce the same words"""
+    o, keys = small_oracle
+    outs = []
+    for flag in (0, 1):
+        lib = os.path.join(ROOT, "tests", "_build", f"libbr_wide_emu_{flag}.so")
+        if not os.path.exists(lib):
+            pytest.skip("emulation libraries not built (run the whole module)")
+        e = C.CDLL(lib)
+        bskw = _convert(e, keys.bsk[:3])
+        glwe = np.random.default_rng(9).integers(0, 2**64, (2, 2048), dtype=np.uint64)
+        ks = np.array([np.uint64(1234) << np.uint64(52), np.uint64(77) << np.uint64(52), np.uint64(4000) << np.uint64(52), 0], np.uint64)
+        got = np.zeros((2, 2048), np.uint64)
+        e.emu_wide_blind_rotate(3, _p(ks), None, _p(glwe), _p(bskw, C.c_double), None, _p(got))
+        outs.append(got)
+    assert np.array_equal(outs[0], outs[1])
+
