@@ -45,6 +45,12 @@
 #ifndef FHESTR_BR_SLIM
 #define FHESTR_BR_SLIM 1
 #endif
+// FHESTR_BR_ABLATE (timing experiments only, results are wrong): 1 = no 32-point codelets, 2 = no transposes and no
+// spectrum exchange (barriers kept), 3 = no key loads, 4 = no inter-pass twiddle loads, 5 = no accumulator gather /
+// store -- where the throughput kernel's step goes when its parts are removed one at a time (profiles/r2_br_ablation.md)
+#ifndef FHESTR_BR_ABLATE
+#define FHESTR_BR_ABLATE 0
+#endif
 
 namespace fhestr {
 
@@ -173,11 +179,15 @@ template <class Ctx>
 FHE_HD void transpose32_half(Ctx& c, double (&v)[32]) {
     const int t = c.lane();
     double* buf = c.xbuf();
+#if FHESTR_BR_ABLATE != 2
 #pragma unroll
     for (int r = 0; r < 32; r++) buf[r * kXPad + t] = v[r];
+#endif
     c.syncwarp();
+#if FHESTR_BR_ABLATE != 2
 #pragma unroll
     for (int r = 0; r < 32; r++) v[r] = buf[t * kXPad + r];
+#endif
     c.syncwarp();
 }
 template <class Ctx>
@@ -191,30 +201,46 @@ FHE_HD void transpose32(Ctx& c, double (&re)[32], double (&im)[32]) {
 template <class Ctx>
 FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* tf) {
     const int t = c.lane();
+#if FHESTR_BR_ABLATE != 1
     fft32_fwd_p1(re, im);
+#endif
 #pragma unroll
     for (int k1 = 0; k1 < 32; k1++) {
+#if FHESTR_BR_ABLATE == 4
+        const cplx w = cplx{0.8 + 0.001 * k1, 0.6};
+#else
         const cplx w = c.ldg(tf + k1 * 32 + t);
+#endif
         const cplx z = cmul(cplx{re[k1], im[k1]}, w);
         re[k1] = z.x; im[k1] = z.y;
     }
     transpose32(c, re, im);
+#if FHESTR_BR_ABLATE != 1
     fft32_fwd_p2(re, im);
+#endif
 }
 
 // inverse: (lane = k1, register k2) -> (lane = n2, register n1).  ti[n2*32 + k1] = conj(Tf(k1,n2)).
 template <class Ctx>
 FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* ti) {
     const int t = c.lane();
+#if FHESTR_BR_ABLATE != 1
     fft32_inv_p1(re, im);
+#endif
 #pragma unroll
     for (int n2 = 0; n2 < 32; n2++) {
+#if FHESTR_BR_ABLATE == 4
+        const cplx w = cplx{0.8 + 0.001 * n2, -0.6};
+#else
         const cplx w = c.ldg(ti + n2 * 32 + t);
+#endif
         const cplx z = cmul(cplx{re[n2], im[n2]}, w);
         re[n2] = z.x; im[n2] = z.y;
     }
     transpose32(c, re, im);
+#if FHESTR_BR_ABLATE != 1
     fft32_inv_p2(re, im);
+#endif
 }
 
 // Fourier BSK layout (engine-private, produced once by the key-conversion kernel):
@@ -239,8 +265,13 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     const uint32_t x0 = (uint32_t)((t - e) & (2 * kN - 1)) << 2;
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
+#if FHESTR_BR_ABLATE == 5
+        re[n1] = digit23_slim((x0 * 2654435761u + n1) - a[n1]);
+        im[n1] = digit23_slim((x0 * 40503u + n1) - a[32 + n1]);
+#else
         re[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1) - a[n1]);
         im[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1 + 4096u) - a[32 + n1]);
+#endif
     }
 #else
 #pragma unroll
@@ -260,14 +291,20 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #pragma unroll
     for (int half = 0; half < 2; half++) {   // 16 spectrum rows at a time: the buffer holds 528 complex points
 #pragma unroll
-        for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{re[half * 16 + q], im[half * 16 + q]};
+        for (int q = 0; q < 16; q++)
+            if (FHESTR_BR_ABLATE != 2) xo[q * 32 + t] = cplx{re[half * 16 + q], im[half * 16 + q]};
         // the first key words of this half do not depend on the partner: request them BEFORE the barrier so that
         // their L2 latency overlaps the wait
         cplx gsv[kBskPrefetch], gov[kBskPrefetch];
 #pragma unroll
         for (int q = 0; q < kBskPrefetch; q++) {
+#if FHESTR_BR_ABLATE == 3
+            gsv[q] = cplx{1e-9 * q, 2e-9};
+            gov[q] = cplx{3e-9, 1e-9 * q};
+#else
             gsv[q] = c.ldg(g + bsk_index(p, half * 16 + q, p, t));
             gov[q] = c.ldg(g + bsk_index(1 - p, half * 16 + q, p, t));
+#endif
         }
 #if FHESTR_BR_L1PF
 #pragma unroll
@@ -280,9 +317,17 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int k2 = half * 16 + q;
+#if FHESTR_BR_ABLATE == 3
+            const cplx gs = cplx{1e-9 * q, 2e-9}, go = cplx{3e-9, 1e-9 * q};
+#else
             const cplx gs = q < kBskPrefetch ? gsv[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(p, k2, p, t));
             const cplx go = q < kBskPrefetch ? gov[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(1 - p, k2, p, t));
+#endif
+#if FHESTR_BR_ABLATE == 2
+            const cplx v = cplx{re[k2] * 0.5, im[k2] * 0.25};
+#else
             const cplx v = xp[q * 32 + t];
+#endif
             const cplx s = cmul(cplx{re[k2], im[k2]}, gs);
             re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
             im[k2] = fma(v.x, go.y, fma(v.y, go.x, s.y));
@@ -294,10 +339,15 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
         const int j = 32 * n1 + t;
+#if FHESTR_BR_ABLATE == 5
+        a[n1] = a[n1] + torus32_conv(re[n1], n1);
+        a[32 + n1] = a[32 + n1] + torus32_conv(im[n1], n1);
+#else
         a[n1] = acc[j] + torus32_conv(re[n1], n1);
         a[32 + n1] = acc[j + kM] + torus32_conv(im[n1], n1);
         acc[j] = a[n1];
         acc[j + kM] = a[32 + n1];
+#endif
     }
     c.syncwarp();
 }
