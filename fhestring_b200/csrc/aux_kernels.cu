@@ -31,6 +31,9 @@ struct ConvCtx {
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ double* xbuf() { return xbuf_; }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+    __device__ __forceinline__ void fp_acquire() {}
+    __device__ __forceinline__ void log_mark(int) {}
+    __device__ __forceinline__ void fp_release() {}
     __device__ __forceinline__ cplx ldg(const cplx* p) const {
         const double2 v = __ldg(reinterpret_cast<const double2*>(p));
         return cplx{v.x, v.y};

@@ -52,7 +52,46 @@
 #define FHESTR_BR_ABLATE 0
 #endif
 
+// FHESTR_BR_BATON (bit mask, 0 = off): FP64 baton between the two PBS of a CTA whose warps sit on the same SM
+// sub-partitions.  Bit 0 = forward pass 1 (+ twiddle), bit 1 = forward pass 2, bit 2 = GGSW product + inverse pass 1
+// (+ twiddle), bit 3 = inverse pass 2.  A stretch whose bit is set is entered through Ctx::fp_acquire() and left through
+// Ctx::fp_release(): the two PBS take strict turns, so that one is in a shared-memory / integer stretch while the other
+// owns the FP64 pipe (independent CTAs only reach that by chance; in lockstep the step is 1.3-1.5 x slower).
+#ifndef FHESTR_BR_BATON
+#define FHESTR_BR_BATON 0
+#endif
+
+// FHESTR_BR_RING=1: the Fourier key reaches the product stage through a shared-memory ring filled by bulk TMA
+// (Ctx::key_wait / key_ld / key_done / key_duty) instead of 16-byte loads from L2: a step's 64 KiB tile is 8 chunks
+// of 4 spectrum rows (8 KiB: the rows of both GGSW rows), consumed in order by every warp of the CTA.
+#ifndef FHESTR_BR_RING
+#define FHESTR_BR_RING 0
+#endif
+// FHESTR_BR_ONE_TWIDDLE=1: the inverse transform multiplies by conj(tf) AFTER its transpose (lane = n2, register k1:
+// the same coalesced rows of the same table the forward reads) instead of by the transposed copy ti before it --
+// same values, same products, half the twiddle footprint in L1.  Off: ptxas then keeps the 32 twiddle loads in flight
+// across the start of the last codelet and spills (200-550 bytes per thread).
+#ifndef FHESTR_BR_ONE_TWIDDLE
+#define FHESTR_BR_ONE_TWIDDLE 0
+#endif
+
+// FHESTR_BR_ACC_SMEM=1: no register copy of the warp's own 64 accumulator words between steps; the prologue reads them
+// back from shared memory (64 more LDS.32 per warp-step).  64 registers fewer: what the ring form needs to stay free
+// of spills (its mbarrier waits split the step into many blocks).
+#ifndef FHESTR_BR_ACC_SMEM
+#define FHESTR_BR_ACC_SMEM FHESTR_BR_RING
+#endif
+
 namespace fhestr {
+
+constexpr int kKeyChunkRows = 4;                       // spectrum rows k2 per ring chunk
+constexpr int kKeyChunks = 32 / kKeyChunkRows;         // chunks per CMUX step
+constexpr int kKeyChunkElems = 2 * kKeyChunkRows * 2 * 32;   // complex words: [GGSW row][k2 in chunk][col][k1] = 8 KiB
+constexpr int kKeyPieceElems = kKeyChunkRows * 2 * 32;       // one GGSW row of a chunk: contiguous in the global layout
+
+constexpr int kBatonPhases = ((FHESTR_BR_BATON >> 0) & 1) + ((FHESTR_BR_BATON >> 1) & 1) + ((FHESTR_BR_BATON >> 2) & 1) + ((FHESTR_BR_BATON >> 3) & 1);
+template <class Ctx> FHE_HD void baton_in(Ctx& c, int bit) { if ((FHESTR_BR_BATON >> bit) & 1) c.fp_acquire(); }
+template <class Ctx> FHE_HD void baton_out(Ctx& c, int bit) { if ((FHESTR_BR_BATON >> bit) & 1) c.fp_release(); }
 
 typedef unsigned long long u64;
 typedef long long i64;
@@ -201,6 +240,8 @@ FHE_HD void transpose32(Ctx& c, double (&re)[32], double (&im)[32]) {
 template <class Ctx>
 FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* tf) {
     const int t = c.lane();
+    c.log_mark(1);
+    baton_in(c, 0);
 #if FHESTR_BR_ABLATE != 1
     fft32_fwd_p1(re, im);
 #endif
@@ -214,33 +255,55 @@ FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
         const cplx z = cmul(cplx{re[k1], im[k1]}, w);
         re[k1] = z.x; im[k1] = z.y;
     }
+    baton_out(c, 0);
+    c.log_mark(2);
     transpose32(c, re, im);
+    c.log_mark(3);
+    baton_in(c, 1);
 #if FHESTR_BR_ABLATE != 1
     fft32_fwd_p2(re, im);
 #endif
+    baton_out(c, 1);
 }
 
-// inverse: (lane = k1, register k2) -> (lane = n2, register n1).  ti[n2*32 + k1] = conj(Tf(k1,n2)).
+// inverse: (lane = k1, register k2) -> (lane = n2, register n1).  ti[n2*32 + k1] = conj(Tf(k1,n2)) = conj(tf[k1*32 + n2]).
 template <class Ctx>
-FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* ti) {
+FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* tf, const cplx* ti) {
     const int t = c.lane();
 #if FHESTR_BR_ABLATE != 1
     fft32_inv_p1(re, im);
 #endif
+#if !FHESTR_BR_ONE_TWIDDLE
 #pragma unroll
     for (int n2 = 0; n2 < 32; n2++) {
-#if FHESTR_BR_ABLATE == 4
-        const cplx w = cplx{0.8 + 0.001 * n2, -0.6};
-#else
         const cplx w = c.ldg(ti + n2 * 32 + t);
-#endif
         const cplx z = cmul(cplx{re[n2], im[n2]}, w);
         re[n2] = z.x; im[n2] = z.y;
     }
+#endif
+    baton_out(c, 2);
+    c.log_mark(6);
     transpose32(c, re, im);
+    c.log_mark(7);
+    baton_in(c, 3);
+#if FHESTR_BR_ONE_TWIDDLE
+    // after the transpose: lane = n2, register k1 -- conj(Tf(k1, n2)) = conj(tf[k1*32 + n2])
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+#if FHESTR_BR_ABLATE == 4
+        const cplx w = cplx{0.8 + 0.001 * k1, 0.6};
+#else
+        const cplx w = c.ldg(tf + k1 * 32 + t);
+#endif
+        const double zr = fma(re[k1], w.x, im[k1] * w.y);
+        const double zi = fma(-re[k1], w.y, im[k1] * w.x);   // = cmul(x, conj w), operation for operation
+        re[k1] = zr; im[k1] = zi;
+    }
+#endif
 #if FHESTR_BR_ABLATE != 1
     fft32_inv_p2(re, im);
 #endif
+    baton_out(c, 3);
 }
 
 // Fourier BSK layout (engine-private, produced once by the key-conversion kernel):
@@ -253,11 +316,12 @@ FHE_HD int bsk_index(int row, int k2, int col, int k1) { return ((row * 32 + k2)
 //   a[0..31]  = ACC[32 n1 + lane], a[32..63] = ACC[32 n1 + lane + M]  (registers, in/out)
 //   c.acc()   = this polynomial's accumulator in shared memory (same values), updated on exit
 template <class Ctx>
-FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* tf, const cplx* ti) {
+FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, int step, const cplx* g, const cplx* tf, const cplx* ti) {
     const int t = c.lane();
     const int p = c.poly();
     acc_t* acc = c.acc();
     double re[32], im[32];
+    c.log_mark(0);
     // rotate, subtract, decompose
 #if FHESTR_BR_SLIM
     // byte offset of coefficient (t - e) mod 2N in the 2N-word negacyclic extension; row n1 adds 128 bytes.  Bit 13
@@ -268,6 +332,9 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #if FHESTR_BR_ABLATE == 5
         re[n1] = digit23_slim((x0 * 2654435761u + n1) - a[n1]);
         im[n1] = digit23_slim((x0 * 40503u + n1) - a[32 + n1]);
+#elif FHESTR_BR_ACC_SMEM
+        re[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1) - acc[32 * n1 + t]);
+        im[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1 + 4096u) - acc[32 * n1 + t + kM]);
 #else
         re[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1) - a[n1]);
         im[n1] = digit23_slim(c.acc_ld_rot(x0 + 128u * n1 + 4096u) - a[32 + n1]);
@@ -282,12 +349,46 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
     }
 #endif
     forward1024(c, re, im, tf);
+    c.log_mark(4);
     // Fourier-domain GGSW product.  The two warps swap their spectra through the transpose buffers (1024 complex
     // points fit in the two matrices) and each forms ITS output polynomial completely:
     //     out_p = D_p * G[p][p] + D_(1-p) * G[1-p][p]
     // the second product accumulates with FMAs, so the step costs 8 FP64 operations per point instead of 10
     cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
     const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
+#if FHESTR_BR_RING
+    (void)g;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {   // 16 spectrum rows at a time: the buffer holds 528 complex points
+#pragma unroll
+        for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{re[half * 16 + q], im[half * 16 + q]};
+        c.log_mark(10 + half * 4);
+        c.pair_sync();
+        c.log_mark(11 + half * 4);
+        if (half == 1) baton_in(c, 2);
+#pragma unroll
+        for (int jc = 0; jc < 16 / kKeyChunkRows; jc++) {
+            const int j = half * (16 / kKeyChunkRows) + jc;      // chunk of this step
+            const auto kc = c.key_wait(step, j);
+#pragma unroll
+            for (int r = 0; r < kKeyChunkRows; r++) {
+                const int q = jc * kKeyChunkRows + r, k2 = half * 16 + q;
+                const cplx gs = c.key_ld(kc, p, r, p, t);
+                const cplx go = c.key_ld(kc, 1 - p, r, p, t);
+                const cplx v = xp[q * 32 + t];
+                const cplx s = cmul(cplx{re[k2], im[k2]}, gs);
+                re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
+                im[k2] = fma(v.x, go.y, fma(v.y, go.x, s.y));
+            }
+            c.key_done(step, j);
+            if (jc > 0) c.key_duty(step, j - 1);     // refill the slot of the chunk before: everyone has left it by now
+        }
+        c.log_mark(12 + half * 4);
+        c.pair_sync();
+        c.key_duty(step, half * (16 / kKeyChunkRows) + 16 / kKeyChunkRows - 1);
+        c.log_mark(13 + half * 4);
+    }
+#else
 #pragma unroll
     for (int half = 0; half < 2; half++) {   // 16 spectrum rows at a time: the buffer holds 528 complex points
 #pragma unroll
@@ -313,7 +414,10 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
             c.prefetch_l1(g + bsk_index(1 - p, half * 16 + q, p, t));
         }
 #endif
+        c.log_mark(10 + half * 4);
         c.pair_sync();
+        c.log_mark(11 + half * 4);
+        if (half == 1) baton_in(c, 2);
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int k2 = half * 16 + q;
@@ -332,9 +436,14 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
             re[k2] = fma(v.x, go.x, fma(-v.y, go.y, s.x));
             im[k2] = fma(v.x, go.y, fma(v.y, go.x, s.y));
         }
+        c.log_mark(12 + half * 4);
         c.pair_sync();
+        c.log_mark(13 + half * 4);
     }
-    inverse1024(c, re, im, ti);
+#endif
+    c.log_mark(5);
+    inverse1024(c, re, im, tf, ti);
+    c.log_mark(8);
     // accumulate into the torus accumulator; keep the new words in registers for the next step
 #pragma unroll
     for (int n1 = 0; n1 < 32; n1++) {
@@ -342,6 +451,9 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #if FHESTR_BR_ABLATE == 5
         a[n1] = a[n1] + torus32_conv(re[n1], n1);
         a[32 + n1] = a[32 + n1] + torus32_conv(im[n1], n1);
+#elif FHESTR_BR_ACC_SMEM
+        acc[j] = acc[j] + torus32_conv(re[n1], n1);
+        acc[j + kM] = acc[j + kM] + torus32_conv(im[n1], n1);
 #else
         a[n1] = acc[j] + torus32_conv(re[n1], n1);
         a[32 + n1] = acc[j + kM] + torus32_conv(im[n1], n1);
@@ -350,6 +462,7 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
 #endif
     }
     c.syncwarp();
+    c.log_mark(9);
 }
 
 // Forward transform of one standard-domain GGSW polynomial (key conversion, once per key)
@@ -413,12 +526,26 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
     c.syncwarp();
     for (int i = 0; i < n; i++) {
         const int e = at[i];
-        if (e == 0) continue;  // X^0 * ACC - ACC == 0: the external product contributes exactly nothing
-        cmux_step(c, a, e, bsk + (size_t)i * kBskStepElems, tf, ti);
+        if (e == 0) {          // X^0 * ACC - ACC == 0: the external product contributes exactly nothing
+            for (int q = 0; q < kBatonPhases; q++) { c.fp_acquire(); c.fp_release(); }   // keep the partner's turns
+#if FHESTR_BR_RING
+#pragma unroll 1
+            for (int j = 0; j < kKeyChunks; j++) {      // keep the CTA's key ring turning
+                (void)c.key_wait(i, j);
+                c.key_done(i, j);
+                if (j % (16 / kKeyChunkRows) != 0) c.key_duty(i, j - 1);
+                if (j % (16 / kKeyChunkRows) == 16 / kKeyChunkRows - 1) c.key_duty(i, j);
+            }
+#endif
+            continue;
+        }
+        cmux_step(c, a, e, i, bsk + (size_t)i * kBskStepElems, tf, ti);
     }
+    c.fp_finish();
+    c.log_mark(-1);
     if (job.out_acc) {
 #pragma unroll
-        for (int m = 0; m < 64; m++) job.out_acc[p * kN + 32 * m + t] = acc_to_u64(a[m]);
+        for (int m = 0; m < 64; m++) job.out_acc[p * kN + 32 * m + t] = acc_to_u64(FHESTR_BR_ACC_SMEM ? acc[32 * m + t] : a[m]);
     }
     if (job.out_lwe) {
         if (p == 0) {

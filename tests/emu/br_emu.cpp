@@ -29,6 +29,16 @@ struct HostCtx {
     void pair_sync() { pair_bar->arrive_and_wait(); }
     cplx ldg(const cplx* p) const { return *p; }
     void prefetch_l1(const cplx*) const {}
+    void fp_acquire() {}
+    void fp_release() {}
+    void fp_finish() {}
+    void log_mark(int) {}
+    // key ring (FHESTR_BR_RING): the emulation reads the chunk straight from the global key
+    const cplx* bsk_ = nullptr;
+    const cplx* key_wait(int step, int j) const { return bsk_ + (size_t)step * kBskStepElems + (size_t)j * kKeyPieceElems; }
+    cplx key_ld(const cplx* kc, int row, int r, int col, int k1) const { return kc[(size_t)row * (kBskStepElems / 2) + (r * 2 + col) * 32 + k1]; }
+    void key_done(int, int) {}
+    void key_duty(int, int) {}
     // slim variant: word ((x >> 2) mod N) of this polynomial's accumulator, negated when bit 13 of the byte offset is set
     acc_t acc_ld_rot(uint32_t x) const {
         const acc_t v = acc_[(x >> 2) & (kN - 1)];
@@ -74,6 +84,7 @@ void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc,
             th.emplace_back([&, w, lane] {
                 HostCtx c{lane, w, acc.data() + w * kN, xbuf.data() + w * kWarpXbufDoubles,
                           xbuf.data() + (1 - w) * kWarpXbufDoubles, at.data(), w ? &wb1 : &wb0, &pb};
+                c.bsk_ = reinterpret_cast<const cplx*>(bsk_f);
                 br_thread_main(c, job, reinterpret_cast<const cplx*>(bsk_f), tf.data(), ti.data());
             });
     for (auto& t : th) t.join();

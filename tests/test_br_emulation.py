@@ -17,6 +17,8 @@ VARIANTS = {
     "first_r1_kernel": ("FHESTR_BR_SLIM=0", "FHESTR_BR_CVT_FP64=0"),
     "all_fp64_conversions": ("FHESTR_BR_CVT_FP64=1", "FHESTR_BR_I2F_FP64=1"),
     "l1_prefetch_and_depth_12": ("FHESTR_BR_L1PF=1", "FHESTR_BR_PREFETCH=12"),
+    "key_ring": ("FHESTR_BR_RING=1",),                   # the product stage reads the key chunk by chunk (Ctx::key_*)
+    "one_twiddle_table": ("FHESTR_BR_ONE_TWIDDLE=1",),   # inverse twiddle after the transpose, from conj(tf)
 }
 
 
