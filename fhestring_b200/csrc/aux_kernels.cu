@@ -38,6 +38,17 @@ struct ConvCtx {
         const double2 v = __ldg(reinterpret_cast<const double2*>(p));
         return cplx{v.x, v.y};
     }
+    // FHESTR_BR_TMEM_TW: the conversion (once per key) reads the twiddle chunk from the table
+    __device__ __forceinline__ void tw_ld(int ch, uint32_t (&r)[32], const cplx* tf) const {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double2 w = __ldg(reinterpret_cast<const double2*>(tf + (ch * 8 + j) * 32 + lane_));
+            r[4 * j] = (uint32_t)__double2loint(w.x); r[4 * j + 1] = (uint32_t)__double2hiint(w.x);
+            r[4 * j + 2] = (uint32_t)__double2loint(w.y); r[4 * j + 3] = (uint32_t)__double2hiint(w.y);
+        }
+    }
+    __device__ __forceinline__ void tw_wait(uint32_t (&)[32]) const {}
+    static __device__ __forceinline__ double tw_word(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
 };
 __global__ void __launch_bounds__(64) bsk_convert_kernel(const u64* bsk_std, int n_polys, const cplx* tf, cplx* out) {
     __shared__ __align__(16) double xb[2][kWarpXbufDoubles];

@@ -46,6 +46,11 @@ constexpr int kSlimSharedBase = 0x400;
 #ifndef FHESTR_BR_RING_SLOTS
 #define FHESTR_BR_RING_SLOTS 4
 #endif
+// FHESTR_BR_CTAS: PBS per SM the register allocation is sized for (4: 255 registers per thread; 5: 200)
+#ifndef FHESTR_BR_CTAS
+#define FHESTR_BR_CTAS 4
+#endif
+constexpr int kCtasPerSm = FHESTR_BR_CTAS / FHESTR_BR_PBS;
 constexpr int kPbsPerCta = FHESTR_BR_PBS;
 constexpr int kRingSlots = FHESTR_BR_RING ? FHESTR_BR_RING_SLOTS : 0;
 constexpr int kChunkBytes = kKeyChunkElems * (int)sizeof(cplx);     // 8 KiB
@@ -55,9 +60,10 @@ constexpr int kPartnerXor = FHESTR_BR_PARTNER_XOR;
 constexpr int kXbufBytes = 2 * kWarpXbufDoubles * 8;   // per PBS: one padded matrix per warp
 // layout: [P x transpose matrices][P x mask][mbarriers][pad][P x (acc0 | acc1)][key ring], the accumulators on 8 KiB-aligned
 // SHARED addresses
-constexpr int kMaskBytes = FHESTR_BR_RING ? 1536 : kAtildeBytes;    // n + 1 <= 768 mask words when the ring needs the room
+constexpr bool kAccAligned = FHESTR_BR_CTAS <= 5;   // six CTAs per SM have no room for the alignment pad: the gather adds instead of or-ing
+constexpr int kMaskBytes = (FHESTR_BR_RING || !kAccAligned) ? 1536 : kAtildeBytes;    // n + 1 <= 768 mask words when the ring needs the room
 constexpr int kSlimFront = kPbsPerCta * (kXbufBytes + kMaskBytes) + (FHESTR_BR_RING ? kMbarBytes : 0);
-constexpr int kSlimPad = (8192 - ((kSlimSharedBase + kSlimFront) & 8191)) & 8191;
+constexpr int kSlimPad = kAccAligned ? (8192 - ((kSlimSharedBase + kSlimFront) & 8191)) & 8191 : 0;
 constexpr int kSlimSmemBytes = kSlimFront + kSlimPad + kPbsPerCta * kAccBytes + kRingSlots * kChunkBytes;  // 39 936 B for one PBS without the ring
 static_assert(kSlimSmemBytes <= 227 * 1024, "one CTA's shared memory");
 
@@ -158,7 +164,8 @@ struct DevCtx {
     // word ((x >> 2) mod N) of the accumulator, negated when bit 13 of the byte offset x is set (negacyclic wrap)
     __device__ __forceinline__ acc_t acc_ld_rot(uint32_t x) const {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(acc_s_ | (x & 0x1ffcu)) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(kAccAligned ? (acc_s_ | (x & 0x1ffcu)) : (acc_s_ + (x & 0x1ffcu))) : "memory");
+        if (FHESTR_BR_ABLATE == 7) return v;
         return (x & 0x2000u) ? 0u - v : v;
     }
     __device__ __forceinline__ int lane() const { return lane_; }
@@ -184,6 +191,38 @@ struct DevCtx {
     __device__ __forceinline__ void fp_finish() {  // the leader takes the follower's last hand-over
         if (FHESTR_BR_BATON != 0 && bar_in_ && leader_) asm volatile("bar.sync %0, 128;" ::"r"(bar_in_));
     }
+    // twiddles in tensor memory (FHESTR_BR_TMEM_TW): words [32 ch, 32 ch + 32) of this lane's 128 = twiddles 8 ch .. 8 ch + 7
+    uint32_t tmem_tw_ = 0;   // TMEM address of this warp's lanes, column 0 of the CTA's allocation
+    __device__ __forceinline__ void tw_ld(int ch, uint32_t (&r)[32], const cplx*) const {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tmem_tw_ + 32u * (uint32_t)ch));
+    }
+    // the loaded registers may be read only after tcgen05.wait::ld; passing them through the statement keeps the
+    // compiler from moving a use above it
+    __device__ __forceinline__ void tw_wait(uint32_t (&r)[32]) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+              "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+              "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+              "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+    }
+    __device__ __forceinline__ void tw_st(int ch, const uint32_t (&r)[32]) const {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+            :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+               "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+               "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+               "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
+               "r"(tmem_tw_ + 32u * (uint32_t)ch) : "memory");
+    }
+    static __device__ __forceinline__ double tw_word(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
     __device__ __forceinline__ void prefetch_l1(const cplx* p) const {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
     }
@@ -207,10 +246,10 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
     c.slot_ = slot;
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
     constexpr uint32_t front = P * (kXbufBytes + kMaskBytes) + (FHESTR_BR_RING ? kMbarBytes : 0);
-    const uint32_t pad = (8192u - ((s0 + front) & 8191u)) & 8191u;
+    const uint32_t pad = kAccAligned ? (8192u - ((s0 + front) & 8191u)) & 8191u : 0u;
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (front + pad + P * kAccBytes + kRingSlots * kChunkBytes > dyn || (FHESTR_BR_RING && A.n + 1 > kMaskBytes / 2)) __trap();   // loud, never a wrong result
+    if (front + pad + P * kAccBytes + kRingSlots * kChunkBytes > dyn || A.n + 1 > kMaskBytes / 2) __trap();   // loud, never a wrong result
     double* xb = reinterpret_cast<double*>(smem + slot * kXbufBytes);
     c.atilde_ = reinterpret_cast<uint16_t*>(smem + P * kXbufBytes + slot * kMaskBytes);
     const uint32_t acc_off = front + pad + slot * kAccBytes + c.poly_ * kN * (uint32_t)sizeof(acc_t);
@@ -253,6 +292,34 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
         if (FHESTR_BR_STAGGER2_NS > 0 && ((c.leader_ ? slot : partner) & (kPartnerXor == 1 ? 2 : 1))) __nanosleep(FHESTR_BR_STAGGER2_NS);
     }
 
+#if FHESTR_BR_TMEM_TW
+    // 128 TMEM columns per CTA (4 CTAs per SM = all 512): warp w owns lanes 32 w .. 32 w + 31, one twiddle word per column
+    {
+        uint32_t* slot_addr = reinterpret_cast<uint32_t*>(c.atilde_);   // the mask buffer is free until br_thread_main fills it
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"((uint32_t)__cvta_generic_to_shared(slot_addr)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(slot_addr);
+        c.tmem_tw_ = tbase + ((uint32_t)(warp & 3) << 21);   // lane field: bits 16.., 32 lanes per warp
+        __syncthreads();                                      // everyone has read the address before the mask is written
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            uint32_t r[32];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double2 w = __ldg(reinterpret_cast<const double2*>(A.tf + (ch * 8 + j) * 32 + c.lane_));
+                r[4 * j] = (uint32_t)__double2loint(w.x); r[4 * j + 1] = (uint32_t)__double2hiint(w.x);
+                r[4 * j + 2] = (uint32_t)__double2loint(w.y); r[4 * j + 3] = (uint32_t)__double2hiint(w.y);
+            }
+            c.tw_st(ch, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+#endif
     BrJobView job;
     job.n = A.n;
     job.ks = A.ks + (size_t)b * (A.n + 1);
@@ -292,16 +359,21 @@ __global__ void __launch_bounds__(64 * P, MB) blind_rotate_kernel(BrBatchArgs A)
 #ifdef FHESTR_BR_PHASELOG
     if (threadIdx.x % 64 == 0 && b < 8192) g_cta_log[b][3] = gtimer();
 #endif
+#if FHESTR_BR_TMEM_TW
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // both warps are done with their columns
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(c.tmem_tw_ & 0xffffu) : "memory");
+#endif
 }
 
 cudaError_t blind_rotate_configure() {
-    if (FHESTR_BR_RING) {   // two 2-PBS CTAs need (nearly) all of the SM's shared memory; the key no longer goes through L1
-        constexpr int ctas = 4 / kPbsPerCta;
+    if (FHESTR_BR_RING || kCtasPerSm > 4) {   // two 2-PBS CTAs need (nearly) all of the SM's shared memory; the key no longer goes through L1
+        constexpr int ctas = kCtasPerSm;
         constexpr int pct = (100 * ctas * (kSlimSmemBytes + 1024) + 228 * 1024 - 1) / (228 * 1024);
-        cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<kPbsPerCta, 4 / kPbsPerCta>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<kPbsPerCta, kCtasPerSm>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
         if (e != cudaSuccess) return e;
     }
-    return cudaFuncSetAttribute(blind_rotate_kernel<kPbsPerCta, 4 / kPbsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlimSmemBytes);
+    return cudaFuncSetAttribute(blind_rotate_kernel<kPbsPerCta, kCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlimSmemBytes);
 }
 
 // Measured (r1, 4096 PBS): one PBS per 64-thread CTA, 4 CTAs per SM at 255 registers is the fastest shape; independent
@@ -310,7 +382,7 @@ cudaError_t blind_rotate_configure() {
 // slower for 1.5x the warps (net 0.8x).  Those variants are gone from the tree (git history: round 1).
 int launch_blind_rotate(const BrBatchArgs& a, cudaStream_t s) {
     if (a.B <= 0) return 0;
-    blind_rotate_kernel<kPbsPerCta, 4 / kPbsPerCta><<<(a.B + kPbsPerCta - 1) / kPbsPerCta, 64 * kPbsPerCta, kSlimSmemBytes, s>>>(a);
+    blind_rotate_kernel<kPbsPerCta, kCtasPerSm><<<(a.B + kPbsPerCta - 1) / kPbsPerCta, 64 * kPbsPerCta, kSlimSmemBytes, s>>>(a);
     return 1;
 }
 

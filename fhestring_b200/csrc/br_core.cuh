@@ -47,7 +47,8 @@
 #endif
 // FHESTR_BR_ABLATE (timing experiments only, results are wrong): 1 = no 32-point codelets, 2 = no transposes and no
 // spectrum exchange (barriers kept), 3 = no key loads, 4 = no inter-pass twiddle loads, 5 = no accumulator gather /
-// store -- where the throughput kernel's step goes when its parts are removed one at a time (profiles/r2_br_ablation.md)
+// store -- where the throughput kernel's step goes when its parts are removed one at a time (profiles/r2_br_ablation.md);
+// with FHESTR_BR_COMPACT: 6 = no twists along n1 (loop 31.8 KB), 7 = also no sign handling in the gather (29.8 KB)
 #ifndef FHESTR_BR_ABLATE
 #define FHESTR_BR_ABLATE 0
 #endif
@@ -80,6 +81,29 @@
 // of spills (its mbarrier waits split the step into many blocks).
 #ifndef FHESTR_BR_ACC_SMEM
 #define FHESTR_BR_ACC_SMEM FHESTR_BR_RING
+#endif
+
+// FHESTR_BR_TMEM_TW=1: a lane's 32 inter-pass twiddles tf[k1*32 + lane] live in TENSOR MEMORY (128 columns of the
+// CTA's TMEM allocation, lane-private: tcgen05.st once per PBS, tcgen05.ld 8 twiddles at a time) instead of being
+// re-read from L1 / L2 in every transform: the 64 LDG.128 per warp-step are 17 % of the kernel's LSU wavefronts, its
+// busiest unit, and TMEM has its own data path.  The inverse multiplies after its transpose (ONE_TWIDDLE), so one set
+// of values serves both directions.  Ctx::tw_ld / tw_wait.
+#ifndef FHESTR_BR_TMEM_TW
+#define FHESTR_BR_TMEM_TW 0
+#endif
+#if FHESTR_BR_TMEM_TW
+#undef FHESTR_BR_ONE_TWIDDLE
+#define FHESTR_BR_ONE_TWIDDLE 1
+#endif
+
+// FHESTR_BR_COMPACT=1: the CMUX step as a ROLLED loop of four passes over ONE copy of the plain DFT-32 codelet
+// (cmux_step_compact below) instead of four different straight-line codelets: the step's code shrinks from 57.7 KB to
+// about the size of the SM's 32 KB instruction cache (profiles/r2_phase_log.md: the straight-line loop streams from
+// the GPC-level instruction cache, which is 91 % busy).  The inverse passes are the forward codelet on swapped
+// real / imaginary parts, the twist along n1 is applied outside the codelet (kFft32Twist*).  Same transform, same
+// spectrum layout, same key.
+#ifndef FHESTR_BR_COMPACT
+#define FHESTR_BR_COMPACT 0
 #endif
 
 namespace fhestr {
@@ -245,6 +269,28 @@ FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
 #if FHESTR_BR_ABLATE != 1
     fft32_fwd_p1(re, im);
 #endif
+#if FHESTR_BR_TMEM_TW
+    {
+        // 8 twiddles (32 words) per tcgen05.ld; the next chunk is in flight while this one is used
+        uint32_t wa[32], wb[32];
+        c.tw_ld(0, wa, tf);
+        c.tw_wait(wa);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            uint32_t (&cur)[32] = (ch & 1) ? wb : wa;
+            uint32_t (&nxt)[32] = (ch & 1) ? wa : wb;
+            if (ch < 3) c.tw_ld(ch + 1, nxt, tf);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k1 = ch * 8 + j;
+                const cplx w = cplx{c.tw_word(cur[4 * j], cur[4 * j + 1]), c.tw_word(cur[4 * j + 2], cur[4 * j + 3])};
+                const cplx z = cmul(cplx{re[k1], im[k1]}, w);
+                re[k1] = z.x; im[k1] = z.y;
+            }
+            if (ch < 3) c.tw_wait(nxt);
+        }
+    }
+#else
 #pragma unroll
     for (int k1 = 0; k1 < 32; k1++) {
 #if FHESTR_BR_ABLATE == 4
@@ -255,6 +301,7 @@ FHE_HD void forward1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
         const cplx z = cmul(cplx{re[k1], im[k1]}, w);
         re[k1] = z.x; im[k1] = z.y;
     }
+#endif
     baton_out(c, 0);
     c.log_mark(2);
     transpose32(c, re, im);
@@ -288,6 +335,28 @@ FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
     baton_in(c, 3);
 #if FHESTR_BR_ONE_TWIDDLE
     // after the transpose: lane = n2, register k1 -- conj(Tf(k1, n2)) = conj(tf[k1*32 + n2])
+#if FHESTR_BR_TMEM_TW
+    {
+        uint32_t wa[32], wb[32];
+        c.tw_ld(0, wa, tf);
+        c.tw_wait(wa);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            uint32_t (&cur)[32] = (ch & 1) ? wb : wa;
+            uint32_t (&nxt)[32] = (ch & 1) ? wa : wb;
+            if (ch < 3) c.tw_ld(ch + 1, nxt, tf);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k1 = ch * 8 + j;
+                const cplx w = cplx{c.tw_word(cur[4 * j], cur[4 * j + 1]), c.tw_word(cur[4 * j + 2], cur[4 * j + 3])};
+                const double zr = fma(re[k1], w.x, im[k1] * w.y);
+                const double zi = fma(-re[k1], w.y, im[k1] * w.x);
+                re[k1] = zr; im[k1] = zi;
+            }
+            if (ch < 3) c.tw_wait(nxt);
+        }
+    }
+#else
 #pragma unroll
     for (int k1 = 0; k1 < 32; k1++) {
 #if FHESTR_BR_ABLATE == 4
@@ -299,6 +368,7 @@ FHE_HD void inverse1024(Ctx& c, double (&re)[32], double (&im)[32], const cplx* 
         const double zi = fma(-re[k1], w.y, im[k1] * w.x);   // = cmul(x, conj w), operation for operation
         re[k1] = zr; im[k1] = zi;
     }
+#endif
 #endif
 #if FHESTR_BR_ABLATE != 1
     fft32_inv_p2(re, im);
@@ -465,6 +535,263 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, int step, const cplx* g, co
     c.log_mark(9);
 }
 
+#ifdef __CUDA_ARCH__
+#define FHESTR_TWIST(i) kFft32TwistDev[i]
+#else
+#define FHESTR_TWIST(i) kFft32TwistHost[i]
+#endif
+
+// FHESTR_BR_TWREG = K (compact loop only): the first K of a lane's 32 inter-pass twiddles tf[k1*32 + lane] stay in
+// registers for the whole blind rotation (4 K registers); the inverse multiplies AFTER its transpose (lane = n2,
+// register k1: the values the forward uses), so one set serves both directions and 2 K of the step's 64 twiddle loads
+// go away.  FHESTR_BR_AREG=1: the accumulation adds to the register copy a[] instead of re-reading the accumulator
+// from shared memory (64 LDS fewer per warp-step, 64 registers live across the passes).  Both trade the registers the
+// compact loop frees (168 instead of 255) for shared-memory / L1 wavefronts: the LSU pipe is this kernel's busiest unit.
+#ifndef FHESTR_BR_TWREG
+#define FHESTR_BR_TWREG 0
+#endif
+#ifndef FHESTR_BR_AREG
+#define FHESTR_BR_AREG 0
+#endif
+// FHESTR_BR_TW_EARLY=1 (with FHESTR_BR_TMEM_TW): the first twiddle chunk is requested from tensor memory BEFORE the
+// pass whose results it multiplies (32 more live registers across the codelet), so its latency is never exposed
+#ifndef FHESTR_BR_TW_EARLY
+#define FHESTR_BR_TW_EARLY 0
+#endif
+// FHESTR_BR_KEY_EARLY=E (compact loop): the first E register-prefetched key rows of the product's first half are
+// requested BEFORE forward pass 2 instead of after it, so that their L2 latency hides behind the codelet (8 E registers
+// live across the loop: the rolled loop cannot scope them to one iteration)
+#ifndef FHESTR_BR_KEY_EARLY
+#define FHESTR_BR_KEY_EARLY 0
+#endif
+constexpr int kTwReg = FHESTR_BR_TWREG;
+
+// multiply the 32 points by the inter-pass twiddles of this lane (registers for k1 < kTwReg, L1 / L2 beyond)
+template <class Ctx>
+FHE_HD void twiddle32(Ctx& c, double (&A)[32], double (&B)[32], const cplx* tf, const cplx (&twr)[kTwReg > 0 ? kTwReg : 1], uint32_t (&wa)[32]) {
+    const int t = c.lane();
+#if FHESTR_BR_TMEM_TW
+    (void)twr; (void)t;
+    uint32_t wb[32];
+#if !FHESTR_BR_TW_EARLY
+    c.tw_ld(0, wa, tf);
+#endif
+    c.tw_wait(wa);
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        uint32_t (&cur)[32] = (ch & 1) ? wb : wa;
+        uint32_t (&nxt)[32] = (ch & 1) ? wa : wb;
+        if (ch < 3) c.tw_ld(ch + 1, nxt, tf);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = ch * 8 + j;
+            const cplx w = cplx{c.tw_word(cur[4 * j], cur[4 * j + 1]), c.tw_word(cur[4 * j + 2], cur[4 * j + 3])};
+            const cplx z = cmul(cplx{A[r], B[r]}, w);
+            A[r] = z.x; B[r] = z.y;
+        }
+        if (ch < 3) c.tw_wait(nxt);
+    }
+#else
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        const cplx w = r < kTwReg ? twr[r < kTwReg ? r : 0] : c.ldg(tf + r * 32 + t);
+        const cplx z = cmul(cplx{A[r], B[r]}, w);
+        A[r] = z.x; B[r] = z.y;
+    }
+#endif
+}
+
+// The same CMUX step with its four 32-point passes rolled into one loop (FHESTR_BR_COMPACT).  (A, B) hold
+// (real, imaginary) parts during the forward passes and (imaginary, real) during the inverse ones: the inverse DFT of x
+// is swap(DFT(swap(x))), and a multiplication by conj(w) in the swapped domain is a multiplication by w, so the passes
+// and the twiddle multiplication of both directions are the SAME instructions.
+//   before the loop: gather + digits + twist exp(+i pi n1/64)
+//   pass 0: DFT over n1, twiddle tf, transpose
+//   pass 1: DFT over n2, spectrum exchange + GGSW product (results written swapped)
+//   pass 2: DFT over k2 (inverse), transpose, twiddle tf (lane = n2, register k1 again)
+//   pass 3: DFT over k1 (inverse)
+//   after the loop: untwist exp(-i pi n1/64), accumulate
+template <class Ctx>
+FHE_HD void cmux_step_compact(Ctx& c, acc_t (&a)[64], int e, int step, const cplx* g, const cplx* tf, const cplx (&twr)[kTwReg > 0 ? kTwReg : 1]) {
+    const int t = c.lane();
+    const int p = c.poly();
+    acc_t* acc = c.acc();
+    double A[32], B[32];
+    (void)step;
+    // the gather consumes the register copy a[] BEFORE the rolled loop and the accumulation rewrites it AFTER it, so
+    // that a[] is dead across the loop (inside it, the compiler would have to keep it alive over every pass)
+    c.log_mark(0);
+    {
+        const uint32_t x0 = (uint32_t)((t - e) & (2 * kN - 1)) << 2;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+            const double dr = digit23_slim(c.acc_ld_rot(x0 + 128u * n1) - a[n1]);
+            const double di = digit23_slim(c.acc_ld_rot(x0 + 128u * n1 + 4096u) - a[32 + n1]);
+            if (n1 == 0 || FHESTR_BR_ABLATE >= 6) { A[n1] = dr; B[n1] = di; }   // ABLATE 6, 7: timing without the twists
+            else {
+                const double cs = FHESTR_TWIST(2 * n1), sn = FHESTR_TWIST(2 * n1 + 1);
+                A[n1] = fma(dr, cs, -(di * sn));
+                B[n1] = fma(dr, sn, di * cs);
+            }
+        }
+    }
+    c.log_mark(1);
+    // FHESTR_BR_COMPACT=1: four iterations over one codelet copy; 2: two iterations (forward, inverse) over two copies
+    uint32_t w0[32];
+#if FHESTR_BR_KEY_EARLY
+    constexpr int kKeyEarly = FHESTR_BR_KEY_EARLY < kBskPrefetch ? FHESTR_BR_KEY_EARLY : kBskPrefetch;   // rows requested early
+    cplx gs0[kKeyEarly], go0[kKeyEarly];
+#endif
+#if FHESTR_BR_COMPACT == 2
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+#if FHESTR_BR_TMEM_TW && FHESTR_BR_TW_EARLY
+        c.tw_ld(0, w0, tf);
+#endif
+        fft32_fwd_p2(A, B);
+        if (h == 0) {
+            twiddle32(c, A, B, tf, twr, w0);
+            c.log_mark(2);
+            transpose32(c, A, B);
+            c.log_mark(3);
+        } else {
+            c.log_mark(6);
+            transpose32(c, A, B);
+            c.log_mark(7);
+            twiddle32(c, A, B, tf, twr, w0);
+        }
+        fft32_fwd_p2(A, B);
+        if (h == 0) {
+            c.log_mark(4);
+            cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
+            const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{A[half * 16 + q], B[half * 16 + q]};
+                cplx gsv[kBskPrefetch], gov[kBskPrefetch];
+#pragma unroll
+                for (int q = 0; q < kBskPrefetch; q++) {
+                    gsv[q] = c.ldg(g + bsk_index(p, half * 16 + q, p, t));
+                    gov[q] = c.ldg(g + bsk_index(1 - p, half * 16 + q, p, t));
+                }
+                c.log_mark(10 + half * 4);
+                c.pair_sync();
+                c.log_mark(11 + half * 4);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int k2 = half * 16 + q;
+                    const cplx gs = q < kBskPrefetch ? gsv[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(p, k2, p, t));
+                    const cplx go = q < kBskPrefetch ? gov[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(1 - p, k2, p, t));
+                    const cplx v = xp[q * 32 + t];
+                    const cplx s = cmul(cplx{A[k2], B[k2]}, gs);
+                    const double zr = fma(v.x, go.x, fma(-v.y, go.y, s.x));
+                    const double zi = fma(v.x, go.y, fma(v.y, go.x, s.y));
+                    A[k2] = zi; B[k2] = zr;      // swapped from here on
+                }
+                c.log_mark(12 + half * 4);
+                c.pair_sync();
+                c.log_mark(13 + half * 4);
+            }
+            c.log_mark(5);
+        }
+    }
+#else
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+#if FHESTR_BR_TMEM_TW && FHESTR_BR_TW_EARLY
+        if ((it & 1) == 0) c.tw_ld(0, w0, tf);
+#endif
+#if FHESTR_BR_KEY_EARLY
+        if (it == 1) {
+#pragma unroll
+            for (int q = 0; q < kKeyEarly; q++) {
+                gs0[q] = c.ldg(g + bsk_index(p, q, p, t));
+                go0[q] = c.ldg(g + bsk_index(1 - p, q, p, t));
+            }
+        }
+#endif
+        fft32_fwd_p2(A, B);
+        if (it == 0) {
+            twiddle32(c, A, B, tf, twr, w0);
+            c.log_mark(2);
+            transpose32(c, A, B);
+            c.log_mark(3);
+        } else if (it == 2) {
+            c.log_mark(6);
+            transpose32(c, A, B);
+            c.log_mark(7);
+            twiddle32(c, A, B, tf, twr, w0);
+        } else if (it == 1) {
+            c.log_mark(4);
+            cplx* xo = reinterpret_cast<cplx*>(c.xbuf());
+            const cplx* xp = reinterpret_cast<const cplx*>(c.xbuf_partner());
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) xo[q * 32 + t] = cplx{A[half * 16 + q], B[half * 16 + q]};
+                cplx gsv[kBskPrefetch], gov[kBskPrefetch];
+#pragma unroll
+                for (int q = 0; q < kBskPrefetch; q++) {
+#if FHESTR_BR_KEY_EARLY
+                    if (half == 0 && q < kKeyEarly) { gsv[q] = gs0[q < kKeyEarly ? q : 0]; gov[q] = go0[q < kKeyEarly ? q : 0]; continue; }
+#endif
+                    gsv[q] = c.ldg(g + bsk_index(p, half * 16 + q, p, t));
+                    gov[q] = c.ldg(g + bsk_index(1 - p, half * 16 + q, p, t));
+                }
+#if FHESTR_BR_L1PF
+#pragma unroll
+                for (int q = kBskPrefetch; q < 16; q++) {
+                    c.prefetch_l1(g + bsk_index(p, half * 16 + q, p, t));
+                    c.prefetch_l1(g + bsk_index(1 - p, half * 16 + q, p, t));
+                }
+#endif
+                c.log_mark(10 + half * 4);
+                c.pair_sync();
+                c.log_mark(11 + half * 4);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int k2 = half * 16 + q;
+                    const cplx gs = q < kBskPrefetch ? gsv[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(p, k2, p, t));
+                    const cplx go = q < kBskPrefetch ? gov[q < kBskPrefetch ? q : 0] : c.ldg(g + bsk_index(1 - p, k2, p, t));
+                    const cplx v = xp[q * 32 + t];
+                    const cplx s = cmul(cplx{A[k2], B[k2]}, gs);
+                    const double zr = fma(v.x, go.x, fma(-v.y, go.y, s.x));
+                    const double zi = fma(v.x, go.y, fma(v.y, go.x, s.y));
+                    A[k2] = zi; B[k2] = zr;      // swapped from here on
+                }
+                c.log_mark(12 + half * 4);
+                c.pair_sync();
+                c.log_mark(13 + half * 4);
+            }
+            c.log_mark(5);
+        }
+    }
+#endif
+    c.log_mark(8);
+#pragma unroll
+    for (int n1 = 0; n1 < 32; n1++) {
+        const int j = 32 * n1 + t;
+        double zr = B[n1], zi = A[n1];
+        if (n1 != 0 && FHESTR_BR_ABLATE < 6) {
+            const double cs = FHESTR_TWIST(2 * n1), sn = FHESTR_TWIST(2 * n1 + 1);
+            zr = fma(B[n1], cs, A[n1] * sn);
+            zi = fma(A[n1], cs, -(B[n1] * sn));
+        }
+#if FHESTR_BR_AREG
+        a[n1] += torus32_conv(zr, n1);
+        a[32 + n1] += torus32_conv(zi, n1);
+#else
+        a[n1] = acc[j] + torus32_conv(zr, n1);
+        a[32 + n1] = acc[j + kM] + torus32_conv(zi, n1);
+#endif
+        acc[j] = a[n1];
+        acc[j + kM] = a[32 + n1];
+    }
+    c.syncwarp();
+    c.log_mark(9);
+}
+
 // Forward transform of one standard-domain GGSW polynomial (key conversion, once per key)
 template <class Ctx>
 FHE_HD void bsk_poly_forward(Ctx& c, const u64* poly, cplx* out_step, int row, int col, const cplx* tf) {
@@ -524,6 +851,12 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
         }
     }
     c.syncwarp();
+#if FHESTR_BR_COMPACT
+    cplx twr[kTwReg > 0 ? kTwReg : 1];
+#pragma unroll
+    for (int r = 0; r < kTwReg; r++) twr[r] = c.ldg(tf + r * 32 + t);
+    (void)ti;
+#endif
     for (int i = 0; i < n; i++) {
         const int e = at[i];
         if (e == 0) {          // X^0 * ACC - ACC == 0: the external product contributes exactly nothing
@@ -539,7 +872,11 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
 #endif
             continue;
         }
+#if FHESTR_BR_COMPACT
+        cmux_step_compact(c, a, e, i, bsk + (size_t)i * kBskStepElems, tf, twr);
+#else
         cmux_step(c, a, e, i, bsk + (size_t)i * kBskStepElems, tf, ti);
+#endif
     }
     c.fp_finish();
     c.log_mark(-1);
@@ -564,7 +901,8 @@ FHE_HD void br_thread_main(Ctx& c, const BrJobView& job, const cplx* bsk, const 
 }
 
 // Twiddle tables shared by the engine and the host emulation:
-//   tf[k1*32 + n2] = exp(+i pi n2 (1-4 k1) / N),  ti[n2*32 + k1] = conj of the same value
+//   tf[k1*32 + n2] = exp(+i pi n2 (1-4 k1) / N),  ti[n2*32 + k1] = conj of the same value (the compact loop reads tf
+//   only: its inverse passes run on swapped real / imaginary parts and multiply after the transpose)
 inline void make_twiddles(cplx* tf, cplx* ti) {
     for (int k1 = 0; k1 < 32; k1++)
         for (int n2 = 0; n2 < 32; n2++) {

@@ -42,6 +42,7 @@ class Prog:
         return name
 
 
+TWIST = [f(math.pi * n / 64) for n in range(R) for f in (math.cos, math.sin)]
 CONST_POOL = []   # distinct |twiddle| values; referenced as FFTC(i) so that DFMA reads them from the constant bank
 
 
@@ -211,6 +212,12 @@ def main():
         "static __constant__ double kFft32ConstDev[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
         "#endif",
         "static const double kFft32ConstHost[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
+        "// twist of the folded negacyclic transform along n1: cos, sin of pi n1 / 64 (the compact loop of br_core.cuh",
+        "// applies it outside the shared plain DFT-32 instead of merging it into a second network)",
+        "#ifdef __CUDACC__",
+        "static __constant__ double kFft32TwistDev[] = {" + ", ".join(repr(v) for v in TWIST) + "};",
+        "#endif",
+        "static const double kFft32TwistHost[] = {" + ", ".join(repr(v) for v in TWIST) + "};",
         "#ifdef __CUDA_ARCH__",
         "#define FFTC(i) kFft32ConstDev[i]",
         "#else",

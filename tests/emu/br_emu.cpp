@@ -29,6 +29,17 @@ struct HostCtx {
     void pair_sync() { pair_bar->arrive_and_wait(); }
     cplx ldg(const cplx* p) const { return *p; }
     void prefetch_l1(const cplx*) const {}
+    // twiddles in tensor memory (FHESTR_BR_TMEM_TW): the emulation reads the 8 twiddles of chunk ch from the table
+    void tw_ld(int ch, uint32_t (&r)[32], const cplx* tf) const {
+        for (int j = 0; j < 8; j++) std::memcpy(&r[4 * j], &tf[(ch * 8 + j) * 32 + lane_], sizeof(cplx));
+    }
+    void tw_wait(uint32_t (&)[32]) const {}
+    static double tw_word(uint32_t lo, uint32_t hi) {
+        const u64 b = ((u64)hi << 32) | lo;
+        double d;
+        std::memcpy(&d, &b, 8);
+        return d;
+    }
     void fp_acquire() {}
     void fp_release() {}
     void fp_finish() {}

@@ -18,7 +18,10 @@ VARIANTS = {
     "all_fp64_conversions": ("FHESTR_BR_CVT_FP64=1", "FHESTR_BR_I2F_FP64=1"),
     "l1_prefetch_and_depth_12": ("FHESTR_BR_L1PF=1", "FHESTR_BR_PREFETCH=12"),
     "key_ring": ("FHESTR_BR_RING=1",),                   # the product stage reads the key chunk by chunk (Ctx::key_*)
-    "one_twiddle_table": ("FHESTR_BR_ONE_TWIDDLE=1",),   # inverse twiddle after the transpose, from conj(tf)
+    "one_twiddle_table": ("FHESTR_BR_ONE_TWIDDLE=1",),
+    "twiddles_in_tensor_memory": ("FHESTR_BR_TMEM_TW=1",),   # chunked twiddle reads (Ctx::tw_ld), inverse twiddle after the transpose
+    "compact_rolled_loop": ("FHESTR_BR_COMPACT=1",),     # four passes over one shared DFT-32 codelet (cmux_step_compact)
+    "compact_register_twiddles": ("FHESTR_BR_COMPACT=1", "FHESTR_BR_TWREG=16", "FHESTR_BR_AREG=1"),   # inverse twiddle after the transpose, from conj(tf)
 }
 
 
