@@ -31,14 +31,11 @@ struct ConvCtx {
     __device__ __forceinline__ int lane() const { return lane_; }
     __device__ __forceinline__ double* xbuf() { return xbuf_; }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
-    __device__ __forceinline__ void fp_acquire() {}
-    __device__ __forceinline__ void log_mark(int) {}
-    __device__ __forceinline__ void fp_release() {}
     __device__ __forceinline__ cplx ldg(const cplx* p) const {
         const double2 v = __ldg(reinterpret_cast<const double2*>(p));
         return cplx{v.x, v.y};
     }
-    // FHESTR_BR_TMEM_TW: the conversion (once per key) reads the twiddle chunk from the table
+    // the blind rotation keeps its twiddles in tensor memory; the conversion (once per key) reads the chunk from the table
     __device__ __forceinline__ void tw_ld(int ch, uint32_t (&r)[32], const cplx* tf) const {
 #pragma unroll
         for (int j = 0; j < 8; j++) {

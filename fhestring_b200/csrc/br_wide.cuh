@@ -255,8 +255,8 @@ FHE_HD void wide_cmux_step(Ctx& c, acc_t (&a)[2][16], int e, int step, const Wid
     for (int p = 0; p < 2; p++)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            re[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);
-            im[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);
+            re[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);
+            im[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);
         }
     wide_forward<2>(c, re, im, K);
     const cplx* key = c.key_wait(step);   // this step's tile (device: shared memory, after the mbarrier wait)
@@ -341,8 +341,8 @@ FHE_HD void wide_cmux_step_pipe(Ctx& c, acc_t (&a)[2][16], int e, int step, cons
 
 #define W_GATHER(p)                                                                              \
     _Pragma("unroll") for (int k = 0; k < 8; k++) {                                              \
-        re[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);                       \
-        im[p][k] = digit23_slim(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);           \
+        re[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);                       \
+        im[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);           \
     }
 #define W_S1(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int j = 0; j < 8; j++) b0[p * kWX1 + j * 128 + t] = cplx{re[p][j], im[p][j]};
 #define W_L1(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int m = 0; m < 8; m++) { const cplx v = b0[p * kWX1 + i1 + 16 * m]; re[p][m] = v.x; im[p][m] = v.y; }

@@ -32,7 +32,6 @@ struct fhestr_engine {
     u64* ks_body = nullptr;
     int ks_path = 0;                   // 0 = tensor cores (IMMA), 1 = CUDA cores (u64 IMAD)
     cplx* tf = nullptr;
-    cplx* ti = nullptr;
     cplx* bsk_w = nullptr;     // the same key in the spectrum order of the latency kernel (br_wide.cuh)
     WideConsts* wide_tab = nullptr;   // [kWT] per-thread transform constants of the latency kernel
     int n_sms = 148;
@@ -222,12 +221,10 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
         CKC(cudaMemsetAsync(e->arena, 0, arena_blocks * (size_t)(kN + 1) * sizeof(u64), e->stream));
     }
     CKC(cudaMalloc(&e->tf, 1024 * sizeof(cplx)));
-    CKC(cudaMalloc(&e->ti, 1024 * sizeof(cplx)));
     {
-        std::vector<cplx> tf(1024), ti(1024);
-        make_twiddles(tf.data(), ti.data());
+        std::vector<cplx> tf(1024);
+        make_twiddles(tf.data());
         CKC(cudaMemcpyAsync(e->tf, tf.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
-        CKC(cudaMemcpyAsync(e->ti, ti.data(), 1024 * sizeof(cplx), cudaMemcpyHostToDevice, e->stream));
         CKC(cudaStreamSynchronize(e->stream));
     }
     e->n_sms = prop.multiProcessorCount;
@@ -265,7 +262,7 @@ void fhestr_engine_destroy(fhestr_engine* e) {
     if (e->peers_attached) fhestr_peer_detach(e);
     cudaFree(e->my_flags);
     if (e->own_arena && e->arena) cudaFree(e->arena);
-    cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf); cudaFree(e->ti);
+    cudaFree(e->bsk_f); cudaFree(e->ksk); cudaFree(e->ksk_corr); cudaFree(e->tf);
     cudaFree(e->bsk_w); cudaFree(e->wide_tab); cudaFree(e->ksk8); cudaFree(e->ks_digits); cudaFree(e->ks_body);
     cudaFree(e->gather_buf); cudaFree(e->luts); cudaFree(e->lut_post); cudaFree(e->d_jobs); cudaFree(e->ks_out); cudaFree(e->d_bytes);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -469,7 +466,7 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         if (e->timing) CK(cudaEventRecord(t.b, e->stream));
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_post = e->lut_post; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
-        br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.n = e->prm.n; br.B = (int)n_pbs;
+        br.bsk = e->bsk_f; br.tf = e->tf; br.n = e->prm.n; br.B = (int)n_pbs;
         br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
         br.n_peers = 0;
         if (e->peers_attached && peer_stores) {
@@ -764,7 +761,7 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
     CK(cudaMemcpyAsync(e->ks_out, ks_host, (size_t)count * (e->prm.n + 1) * sizeof(u64), cudaMemcpyHostToDevice, e->stream));
     BrBatchArgs br{};
     br.ks = e->ks_out; br.luts = e->luts; br.lut_ids = d_ids; br.jobs = nullptr; br.arena = e->arena;
-    br.bsk = e->bsk_f; br.tf = e->tf; br.ti = e->ti; br.init_acc = d_init; br.out_acc = d_out;
+    br.bsk = e->bsk_f; br.tf = e->tf; br.init_acc = d_init; br.out_acc = d_out;
     br.n = e->prm.n; br.B = (int)count;
     br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
     e->launches += use_wide(e, count) ? launch_wide(e, br, count) : launch_blind_rotate(br, e->stream);

@@ -1,19 +1,22 @@
 #!/usr/bin/env python3
-"""Generate fft32_gen.cuh: straight-line, register-resident 32-point transforms for the four-step
-negacyclic FFT (1024 complex points = 32 x 32) used by the blind-rotation kernel.
+"""Generate fft32_gen.cuh: the straight-line, register-resident 32-point transform of the four-step
+negacyclic FFT (1024 complex points = 32 x 32) used by the blind-rotation kernel, and the table of its
+twist along n1.
 
-Every transform is a Cooley-Tukey network written as polynomial evaluation: the 32 inputs are the
+The transform is a Cooley-Tukey network written as polynomial evaluation: the 32 inputs are the
 coefficients of c(x) and the outputs are c(x_k) at the 32 roots of x^32 = rho.  One stage reduces
 c modulo (x^m - r) and (x^m + r) with r = sqrt(rho), i.e. butterflies (a, b) -> (a + r b, a - r b)
 with ONE twiddle per sub-block; a general butterfly is 6 FMAs (a - r b is formed as 2a - (a + r b)),
 a trivial one (r = 1, i) is 4 add/sub.  All twiddles are literals, so they live in the constant
 bank and no twiddle registers are needed.
 
-  rho = i  (NET_I): merged-twist first pass, evaluation at u_k = exp(i pi (1-4k)/64)   480 FMAs
-  rho = 1  (NET_1): plain DFT-32 at exp(-/+ 2 pi i k / 32)                              388 ops
+  rho = 1: plain DFT-32 at exp(-2 pi i k / 32), 388 ops -- the ONE codelet of the kernel's rolled loop: all four
+  passes of a CMUX step run it (the inverse passes on swapped real / imaginary parts), and the twist exp(i pi n1/64)
+  of the folded transform is applied outside it from kFft32Twist*.  (Round 1 generated four networks, two of them with
+  the twist merged in: 480 + 388 + 388 + 512 ops, 57.7 KB of straight-line loop.)
 
 Outputs are returned in NATURAL index order (the permutation is free: pure register renaming).
-The script checks every emitted network numerically against the dense DFT matrix before writing.
+The script checks the emitted network numerically against the dense DFT matrix before writing.
 
 Run:  python gen_fft32.py   (writes fft32_gen.cuh next to this file; the output is committed)
 """
@@ -170,18 +173,8 @@ def main():
     x = rng.standard_normal(R) + 1j * rng.standard_normal(R)
     funcs = []
     specs = [
-        # forward pass 1: A[k1] = sum_n1 c[n1] u_k1^n1, u_k1 = exp(i pi (1-4 k1)/64); roots of x^32 = i
-        ("fft32_fwd_p1", math.pi / 2, lambda k: math.pi * (1 - 4 * k) / 64, None,
-         "forward pass 1 (merged twist): out[k] = sum_n in[n] * exp(i*pi*(1-4k)*n/64)"),
-        # forward pass 2: D[k2] = sum_n2 B[n2] V^(n2 k2), V = exp(-2 pi i/32)
-        ("fft32_fwd_p2", 0.0, lambda k: -2 * math.pi * k / 32, None,
-         "forward pass 2: out[k] = sum_n in[n] * exp(-2*pi*i*k*n/32)"),
-        # inverse pass 1: E[n2] = sum_k2 Y[k2] V^(-n2 k2)
-        ("fft32_inv_p1", 0.0, lambda k: 2 * math.pi * k / 32, None,
-         "inverse pass 1: out[k] = sum_n in[n] * exp(+2*pi*i*k*n/32)"),
-        # inverse pass 2: c[n1] = exp(-i pi n1/64) sum_k1 F[k1] V^(-n1 k1)
-        ("fft32_inv_p2", 0.0, lambda k: 2 * math.pi * k / 32, lambda k: -math.pi * k / 64,
-         "inverse pass 2 (+untwist): out[k] = exp(-i*pi*k/64) * sum_n in[n] * exp(+2*pi*i*k*n/32)"),
+        ("fft32_dft", 0.0, lambda k: -2 * math.pi * k / 32, None,
+         "plain DFT-32: out[k] = sum_n in[n] * exp(-2*pi*i*k*n/32)"),
     ]
     for name, rho, root, post, doc in specs:
         src, prog, final = build(name, rho, root, post, doc)
@@ -194,8 +187,8 @@ def main():
         print(f"{name}: {prog.ops} ops, max err {err:.2e}")
         funcs.append(src)
     hdr = [
-        "// GENERATED by gen_fft32.py -- do not edit.  32-point register-resident transforms for the",
-        "// four-step (32 x 32) negacyclic FFT of the blind-rotation kernel.  See gen_fft32.py.",
+        "// GENERATED by gen_fft32.py -- do not edit.  The 32-point register-resident transform of the",
+        "// four-step (32 x 32) negacyclic FFT of the blind-rotation kernel and its twist table.  See gen_fft32.py.",
         "#pragma once",
         "#ifndef FHE_HD",
         "#ifdef __CUDACC__",
@@ -212,8 +205,8 @@ def main():
         "static __constant__ double kFft32ConstDev[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
         "#endif",
         "static const double kFft32ConstHost[] = {" + ", ".join(repr(c) for c in CONST_POOL) + "};",
-        "// twist of the folded negacyclic transform along n1: cos, sin of pi n1 / 64 (the compact loop of br_core.cuh",
-        "// applies it outside the shared plain DFT-32 instead of merging it into a second network)",
+        "// twist of the folded negacyclic transform along n1: cos, sin of pi n1 / 64 (br_core.cuh applies it outside the",
+        "// shared plain DFT-32 instead of merging it into a second network)",
         "#ifdef __CUDACC__",
         "static __constant__ double kFft32TwistDev[] = {" + ", ".join(repr(v) for v in TWIST) + "};",
         "#endif",

@@ -17,8 +17,7 @@ struct BrBatchArgs {
     const fhestr_job* jobs;   // [B] device job list (dst + lut) or nullptr
     u64* arena;               // [blocks][N+1]
     const cplx* bsk;          // Fourier BSK, engine layout
-    const cplx* tf;
-    const cplx* ti;
+    const cplx* tf;           // inter-pass twiddles of the throughput kernel, [32 k1][32 n2]
     const u64* init_acc;      // optional [B][2][N]
     u64* out_acc;             // optional [B][2][N]
     u64* peer_arena[7];       // arenas of the other ranks (cudaIpc-mapped), n_peers of them

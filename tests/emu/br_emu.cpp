@@ -28,8 +28,7 @@ struct HostCtx {
     void syncwarp() { warp_bar->arrive_and_wait(); }
     void pair_sync() { pair_bar->arrive_and_wait(); }
     cplx ldg(const cplx* p) const { return *p; }
-    void prefetch_l1(const cplx*) const {}
-    // twiddles in tensor memory (FHESTR_BR_TMEM_TW): the emulation reads the 8 twiddles of chunk ch from the table
+    // the device keeps the twiddles in tensor memory; the emulation reads the 8 twiddles of chunk ch from the table
     void tw_ld(int ch, uint32_t (&r)[32], const cplx* tf) const {
         for (int j = 0; j < 8; j++) std::memcpy(&r[4 * j], &tf[(ch * 8 + j) * 32 + lane_], sizeof(cplx));
     }
@@ -40,17 +39,7 @@ struct HostCtx {
         std::memcpy(&d, &b, 8);
         return d;
     }
-    void fp_acquire() {}
-    void fp_release() {}
-    void fp_finish() {}
-    void log_mark(int) {}
-    // key ring (FHESTR_BR_RING): the emulation reads the chunk straight from the global key
-    const cplx* bsk_ = nullptr;
-    const cplx* key_wait(int step, int j) const { return bsk_ + (size_t)step * kBskStepElems + (size_t)j * kKeyPieceElems; }
-    cplx key_ld(const cplx* kc, int row, int r, int col, int k1) const { return kc[(size_t)row * (kBskStepElems / 2) + (r * 2 + col) * 32 + k1]; }
-    void key_done(int, int) {}
-    void key_duty(int, int) {}
-    // slim variant: word ((x >> 2) mod N) of this polynomial's accumulator, negated when bit 13 of the byte offset is set
+    // word ((x >> 2) mod N) of this polynomial's accumulator, negated when bit 13 of the byte offset is set
     acc_t acc_ld_rot(uint32_t x) const {
         const acc_t v = acc_[(x >> 2) & (kN - 1)];
         return (x & 0x2000u) ? (acc_t)0 - v : v;
@@ -61,8 +50,8 @@ extern "C" {
 
 // bsk_std: [n][2 rows][2 cols][N] u64 (pbs_level == 1).  out: [n][kBskStepElems] complex
 void emu_convert_bsk(int n, const u64* bsk_std, double* out) {
-    std::vector<cplx> tf(1024), ti(1024);
-    make_twiddles(tf.data(), ti.data());
+    std::vector<cplx> tf(1024);
+    make_twiddles(tf.data());
     std::vector<double> xbuf(kWarpXbufDoubles);
     std::barrier<> wb(32);
     std::vector<std::thread> th;
@@ -82,8 +71,8 @@ void emu_convert_bsk(int n, const u64* bsk_std, double* out) {
 // one PBS blind rotation; bsk_f from emu_convert_bsk.  init_acc/out_lwe/out_acc may be null.
 void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc, const double* bsk_f,
                       u64* out_lwe, u64* out_acc) {
-    std::vector<cplx> tf(1024), ti(1024);
-    make_twiddles(tf.data(), ti.data());
+    std::vector<cplx> tf(1024);
+    make_twiddles(tf.data());
     std::vector<acc_t> acc(2 * kN);
     std::vector<double> xbuf(2 * kWarpXbufDoubles);
     std::vector<uint16_t> at(n + 64);
@@ -95,8 +84,7 @@ void emu_blind_rotate(int n, const u64* ks, const u64* lut, const u64* init_acc,
             th.emplace_back([&, w, lane] {
                 HostCtx c{lane, w, acc.data() + w * kN, xbuf.data() + w * kWarpXbufDoubles,
                           xbuf.data() + (1 - w) * kWarpXbufDoubles, at.data(), w ? &wb1 : &wb0, &pb};
-                c.bsk_ = reinterpret_cast<const cplx*>(bsk_f);
-                br_thread_main(c, job, reinterpret_cast<const cplx*>(bsk_f), tf.data(), ti.data());
+                br_thread_main(c, job, reinterpret_cast<const cplx*>(bsk_f), tf.data());
             });
     for (auto& t : th) t.join();
 }

@@ -11,17 +11,11 @@ import pytest
 from conftest import ROOT, monomial_mul
 
 
-# every build of the thread program: the default kernel and the experimental FHESTR_BR_* variants (br_core.cuh)
+# every build of the thread program: the default kernel and the settings of its two compile-time knobs (br_core.cuh)
 VARIANTS = {
-    "default": (),   # aligned accumulator + every 4th torus conversion on the FP64 pipe
-    "first_r1_kernel": ("FHESTR_BR_SLIM=0", "FHESTR_BR_CVT_FP64=0"),
-    "all_fp64_conversions": ("FHESTR_BR_CVT_FP64=1", "FHESTR_BR_I2F_FP64=1"),
-    "l1_prefetch_and_depth_12": ("FHESTR_BR_L1PF=1", "FHESTR_BR_PREFETCH=12"),
-    "key_ring": ("FHESTR_BR_RING=1",),                   # the product stage reads the key chunk by chunk (Ctx::key_*)
-    "one_twiddle_table": ("FHESTR_BR_ONE_TWIDDLE=1",),
-    "twiddles_in_tensor_memory": ("FHESTR_BR_TMEM_TW=1",),   # chunked twiddle reads (Ctx::tw_ld), inverse twiddle after the transpose
-    "compact_rolled_loop": ("FHESTR_BR_COMPACT=1",),     # four passes over one shared DFT-32 codelet (cmux_step_compact)
-    "compact_register_twiddles": ("FHESTR_BR_COMPACT=1", "FHESTR_BR_TWREG=16", "FHESTR_BR_AREG=1"),   # inverse twiddle after the transpose, from conj(tf)
+    "default": (),                                        # no torus conversion on the FP64 pipe, 8 key rows prefetched
+    "fp64_conversions": ("FHESTR_BR_CVT_FP64=1",),        # every torus conversion by the 1.5 * 2^52 trick
+    "every_4th_fp64_depth_12": ("FHESTR_BR_CVT_FP64=4", "FHESTR_BR_PREFETCH=12"),
 }
 
 
