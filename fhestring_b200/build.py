@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfhestr_engine.so")
-SOURCES = ["engine.cu", "blind_rotate.cu", "blind_rotate_wide.cu", "keyswitch.cu", "keyswitch_mma.cu", "aux_kernels.cu", "client.cpp", "graph.cpp", "strings.cpp", "graph_capi.cpp"]
+SOURCES = ["engine.cu", "blind_rotate.cu", "blind_rotate_wide.cu", "keyswitch.cu", "keyswitch_tc.cu", "aux_kernels.cu", "client.cpp", "graph.cpp", "strings.cpp", "graph_capi.cpp"]
 HEADERS = ["kernels.cuh", "br_core.cuh", "br_wide.cuh", "fft32_gen.cuh", "graph.h", "strings.h", os.path.join("..", "..", "include", "fhestr_engine.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -30,7 +30,7 @@ struct fhestr_engine {
     unsigned char* ksk8 = nullptr;     // limb matrix for the tensor-core keyswitch
     unsigned char* ks_digits = nullptr;
     u64* ks_body = nullptr;
-    int ks_path = 0;                   // 0 = tensor cores (IMMA), 1 = CUDA cores (u64 IMAD)
+    int ks_path = 0;                   // 0 = tensor cores (tcgen05 kind::i8), 1 = CUDA cores (u64 IMAD)
     cplx* tf = nullptr;
     cplx* bsk_w = nullptr;     // the same key in the spectrum order of the latency kernel (br_wide.cuh)
     WideConsts* wide_tab = nullptr;   // [kWT] per-thread transform constants of the latency kernel
@@ -244,7 +244,7 @@ int fhestr_engine_create(const fhestr_params* p, int device, uint64_t arena_bloc
     CKC(cudaMalloc(&e->ksk, (size_t)kN * p->ks_level * (p->n + 1) * sizeof(u64)));
     CKC(cudaMalloc(&e->ksk_corr, (size_t)(p->n + 1) * sizeof(u64)));
     CKC(cudaMalloc(&e->ksk8, (size_t)ks_cols_padded(p->n) * 8 * kN * p->ks_level));
-    CKC(keyswitch_mma_configure());
+    CKC(keyswitch_tc_configure());
     if (p->ks_base_log > 7) e->ks_path = 1;   // unsigned digits must fit a byte
     CKC(blind_rotate_configure());
     CKC(keyswitch_configure());
@@ -462,7 +462,9 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         }
         KsBatchArgs ks{d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_pbs,
                        e->prm.ks_base_log, e->prm.ks_level, e->ksk8, e->ks_digits, e->ks_body};
-        e->launches += e->ks_path == 0 ? launch_keyswitch_mma(ks, e->stream) : launch_keyswitch(ks, e->stream);
+        const int ks_launches = e->ks_path == 0 ? launch_keyswitch_tc(ks, e->stream) : launch_keyswitch(ks, e->stream);
+        if (ks_launches == 0 && n_pbs > 0) return fail(e, FHESTR_E_CUDA, "keyswitch: the TMA tensor maps could not be encoded");
+        e->launches += ks_launches;
         if (e->timing) CK(cudaEventRecord(t.b, e->stream));
         BrBatchArgs br{};
         br.ks = e->ks_out; br.luts = e->luts; br.lut_post = e->lut_post; br.lut_ids = nullptr; br.jobs = d_jobs; br.arena = e->arena;
@@ -731,7 +733,9 @@ int fhestr_debug_keyswitch(fhestr_engine* e, const fhestr_job* jobs, uint32_t n_
     CK(cudaMemcpyAsync(e->d_jobs, jobs, (size_t)n_jobs * sizeof(fhestr_job), cudaMemcpyHostToDevice, e->stream));
     KsBatchArgs ks{e->d_jobs, e->arena, e->ksk, e->ksk_corr, e->ks_out, e->prm.n, (int)n_jobs,
                    e->prm.ks_base_log, e->prm.ks_level, e->ksk8, e->ks_digits, e->ks_body};
-    e->launches += e->ks_path == 0 ? launch_keyswitch_mma(ks, e->stream) : launch_keyswitch(ks, e->stream);
+    const int ks_launches = e->ks_path == 0 ? launch_keyswitch_tc(ks, e->stream) : launch_keyswitch(ks, e->stream);
+    if (ks_launches == 0 && n_jobs > 0) return fail(e, FHESTR_E_CUDA, "keyswitch: the TMA tensor maps could not be encoded");
+    e->launches += ks_launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host_out, e->ks_out, (size_t)n_jobs * (e->prm.n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

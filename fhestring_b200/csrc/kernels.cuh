@@ -35,7 +35,7 @@ struct KsBatchArgs {
     const u64* ksk_corr;      // [n+1]  2^(base_log-1) * sum_{i,lvl} ksk[i][lvl][c]
     u64* ks_out;              // [B][n+1]
     int n, B, base_log, level;
-    // tensor-core path (keyswitch_mma.cu)
+    // tensor-core path (keyswitch_tc.cu)
     const unsigned char* ksk8;   // [cols_padded*8][N*level] limb matrix, K-major
     unsigned char* ks_digits;    // [rows padded to 128][N*level] unsigned digits
     u64* ks_body;                // [B]
@@ -53,9 +53,9 @@ int launch_blind_rotate_wide2(const BrBatchArgs& a, cudaStream_t s);
 cudaError_t blind_rotate_wide_configure();
 int launch_bsk_convert_wide(const u64* bsk_std, int n, const WideConsts* tab, cplx* out, cudaStream_t s);
 cudaError_t keyswitch_configure();  // opt in to the large dynamic shared memory carve-out
-// the same on the tensor cores (IMMA u8 x u8 -> s32 limb-split GEMM); bit-identical results
-int launch_keyswitch_mma(const KsBatchArgs& a, cudaStream_t s);
-cudaError_t keyswitch_mma_configure();
+// the same on the tensor cores (tcgen05.mma kind::i8 u8 x u8 -> s32 limb-split GEMM, TMA-fed; keyswitch_tc.cu); bit-identical results
+int launch_keyswitch_tc(const KsBatchArgs& a, cudaStream_t s);
+cudaError_t keyswitch_tc_configure();
 int launch_ksk_limbs(const u64* ksk, int K, int n, unsigned char* out, cudaStream_t s);
 int ks_cols_padded(int n);
 size_t ks_digit_rows(size_t B);

@@ -151,7 +151,7 @@ class Engine:
         self._ck(self.lib.fhestr_set_br_mode(self.h, C.c_int(mode), C.c_int(wide_max_jobs)))
 
     def set_keyswitch_path(self, path: int):
-        """0 = tensor cores (IMMA limb-split GEMM, default), 1 = CUDA cores"""
+        """0 = tensor cores (tcgen05 kind::i8 limb-split GEMM, default), 1 = CUDA cores"""
         self._ck(self.lib.fhestr_set_keyswitch_path(self.h, C.c_int(path)))
 
     def set_timing(self, enable: bool):

@@ -247,7 +247,7 @@ uint64_t fhestr_kernel_launches(const fhestr_engine* e);
  * pair form (tests, measurements).  All kernels compute the same function; their outputs are different valid
  * ciphertexts of the same plaintext (different f64 FFT orders), see DESIGN.md. */
 int fhestr_set_br_mode(fhestr_engine* e, int mode, int wide_max_jobs);
-/* keyswitch implementation: 0 = tensor cores (u8 limb-split IMMA GEMM, default), 1 = CUDA cores (u64 IMAD);
+/* keyswitch implementation: 0 = tensor cores (u8 limb-split GEMM on tcgen05.mma kind::i8, default), 1 = CUDA cores (u64 IMAD);
  * both are exact and produce identical words */
 int fhestr_set_keyswitch_path(fhestr_engine* e, int path);
 

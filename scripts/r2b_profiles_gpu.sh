@@ -11,3 +11,6 @@ echo "launch list rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:blind_rotate_kernel -s 3 -c 1 -f -o $O/prof_r2b_blind_rotate $BENCH > $O/r2b_prof_ncu2.log 2>&1
 echo "throughput kernel rc=$?"
 ncu -i $O/prof_r2b_blind_rotate.ncu-rep --page raw --csv > $O/r2b_blind_rotate_ncu_raw.csv 2>/dev/null
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:ks_gemm_tc_kernel -s 3 -c 1 -f -o $O/prof_r2b_ks_gemm_tc $BENCH > $O/r2b_prof_ncu3.log 2>&1
+echo "keyswitch GEMM rc=$?"
+ncu -i $O/prof_r2b_ks_gemm_tc.ncu-rep --page raw --csv > $O/r2b_ks_gemm_tc_ncu_raw.csv 2>/dev/null

@@ -105,7 +105,7 @@ def test_keyswitch_ragged_batches_and_linear_terms(small_engine, small_oracle, c
 
 @pytest.mark.parametrize("count", [1, 9, 127, 128, 129, 300])
 def test_keyswitch_tensor_core_and_cuda_core_paths_identical(full_engine, full_oracle, count):
-    """K1 as an IMMA limb-split GEMM (default) and as the u64 IMAD kernel: same words, at the real parameters,
+    """K1 as a tcgen05 kind::i8 limb-split GEMM (default) and as the u64 IMAD kernel: same words, at the real parameters,
     around the 128-row GEMM tile; and both equal the oracle on a few rows"""
     from fhestring_b200.engine import make_jobs
     o, keys = full_oracle
