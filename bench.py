@@ -403,6 +403,23 @@ def strings_leg(ctx, steps, cpu_rate):
     return out
 
 
+def _tensor_side(pbs_per_launch, ks_ms_per_launch):
+    """keyswitch (ks_digits_kernel + ks_gemm_tc_kernel) per launch against the tensor peak: MEASURED_PEAKS.json's dense bf16
+    figure x 2 (the int8 rate of B200's tensor cores is twice the bf16 rate), else nominal 4 500 TOP/s"""
+    if ks_ms_per_launch <= 0:
+        return None
+    ops = 2.0 * pbs_per_launch * (742 + 1) * 8 * 2048 * 5          # M x (n + 1) limb columns x K, multiply + add
+    peak, src = 4500.0, "nominal dense int8"
+    try:
+        peak = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        src = "2 x MEASURED_PEAKS.json bf16_tflops"
+    except Exception:
+        pass
+    achieved = ops / (ks_ms_per_launch * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "ks_gemm_tc_kernel (+ ks_digits_kernel)", "achieved": achieved, "peak": peak,
+            "unit": "TOP/s", "frac": achieved / peak, "peak_source": src}
+
+
 def _hbm_side(traffic_bytes, ms_per_launch):
     """DRAM traffic of one blind-rotation launch (ncu) over its duration, against MEASURED_PEAKS.json's hbm_gbs"""
     if not traffic_bytes or ms_per_launch <= 0:
@@ -614,6 +631,9 @@ def main():
                 "peak_source": "DFMA microbenchmark measured in this run (fhestr_measure_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s",
                 "keyswitch_ms_per_launch": ks_ms / max(1, br_launches),
+                # the second kernel pair of a step against ITS roofline: the limb-split GEMM on tcgen05.mma kind::i8
+                # (u8 MACs of the real 743 x 8 limb columns; the time includes the digits kernel in front of the GEMM)
+                "keyswitch": _tensor_side(br_pbs / max(1, br_launches), ks_ms / max(1, br_launches)),
                 "kernel_share_of_step": br_ms / ms_total,
                 # why the bound is FP64 and not HBM: the same kernel against the measured copy bandwidth
                 "hbm": _hbm_side(traffic, br_avg_ms),

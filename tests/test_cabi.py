@@ -43,3 +43,37 @@ def test_no_cpu_fallback_without_gpu(build_lib):
     from fhestring_b200.engine import Engine, EngineError
     with pytest.raises(EngineError, match="no usable CUDA device|no CPU fallback"):
         Engine(arena_blocks=4)
+
+
+# which Blackwell units each kernel is built on, read from the shipped library's SASS (cuobjdump is part of the toolkit
+# that built it): a rebuild that silently drops the tensor-memory twiddles, the tcgen05 GEMM or the bulk-TMA key ring
+# still passes every numerical test, so the instruction mix is pinned here
+SASS_FEATURES = {
+    "blind_rotate_kernel": ["LDTM", "STTM", "UTCATOMSWS", "DFMA"],            # tcgen05.ld / st / alloc, FP64 FMA
+    "ks_gemm_tc_kernel": ["UTCIMMA", "UTMALDG", "UTCBAR", "LDTM", "SYNCS"],   # tcgen05.mma kind::i8, TMA, tcgen05.commit
+    "blind_rotate_wide_kernel": ["UBLKCP", "SYNCS", "DFMA"],                  # bulk TMA key tiles + mbarriers
+    "blind_rotate_wide2_kernel": ["UBLKCP", "SYNCS", "DFMA"],
+}
+
+
+def test_kernels_use_the_blackwell_units_they_claim(build_lib):
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", build_lib], capture_output=True, text=True, check=True).stdout
+    bodies, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            bodies[name] = []
+        elif name:
+            bodies[name].append(line)
+    for kernel, mnemonics in SASS_FEATURES.items():
+        hits = [k for k in bodies if kernel + "E" in k or kernel + "I" in k]
+        assert hits, f"{kernel} not found in the library's SASS"
+        text = "\n".join(bodies[hits[0]])
+        for mn in mnemonics:
+            assert re.search(r"\b" + mn, text), f"{kernel}: no {mn} instruction in its SASS"
+        assert "sm_100a" in sass or "sm_100" in sass
