@@ -62,16 +62,8 @@ FHE_HD int wide_delta(int o) {
     return d[o];
 }
 
-// FHESTR_WIDE_ABLATE (timing experiments only, results are wrong): 1 = no butterflies, 2 = no exchange loads/stores,
-// 3 = no key reads -- where a step's time goes when the phases are removed one at a time (profiles/r2_wide_ablation.md)
-#ifndef FHESTR_WIDE_ABLATE
-#define FHESTR_WIDE_ABLATE 0
-#endif
 // forward butterfly (a, b) -> (a + w b, a - w b): 6 FMAs (a - w b = 2a - (a + w b))
 FHE_HD void w_bfly(double& ar, double& ai, double& br, double& bi, double wr, double wi) {
-#if FHESTR_WIDE_ABLATE == 1
-    return;
-#endif
     const double x = fma(wr, br, ar);
     const double pr = fma(-wi, bi, x);
     const double y = fma(wr, bi, ai);
@@ -83,9 +75,6 @@ FHE_HD void w_bfly(double& ar, double& ai, double& br, double& bi, double wr, do
 }
 // inverse (un-normalised): (p, q) -> (p + q, conj(w) (p - q)),  w = the forward twiddle
 FHE_HD void w_ibfly(double& pr, double& pi, double& qr, double& qi, double wr, double wi) {
-#if FHESTR_WIDE_ABLATE == 1
-    return;
-#endif
     const double dr = pr - qr, di = pi - qi;
     pr = pr + qr;
     pi = pi + qi;
@@ -344,27 +333,27 @@ FHE_HD void wide_cmux_step_pipe(Ctx& c, acc_t (&a)[2][16], int e, int step, cons
         re[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k) - a[p][k]);                       \
         im[p][k] = digit23(c.acc_ld_rot(p, x0 + 512u * k + 4096u) - a[p][8 + k]);           \
     }
-#define W_S1(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int j = 0; j < 8; j++) b0[p * kWX1 + j * 128 + t] = cplx{re[p][j], im[p][j]};
-#define W_L1(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int m = 0; m < 8; m++) { const cplx v = b0[p * kWX1 + i1 + 16 * m]; re[p][m] = v.x; im[p][m] = v.y; }
-#define W_S2(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int l = 0; l < 8; l++) b1[p * kWX2 + i2w + l * 17] = cplx{re[p][l], im[p][l]};
+#define W_S1(p) _Pragma("unroll") for (int j = 0; j < 8; j++) b0[p * kWX1 + j * 128 + t] = cplx{re[p][j], im[p][j]};
+#define W_L1(p) _Pragma("unroll") for (int m = 0; m < 8; m++) { const cplx v = b0[p * kWX1 + i1 + 16 * m]; re[p][m] = v.x; im[p][m] = v.y; }
+#define W_S2(p) _Pragma("unroll") for (int l = 0; l < 8; l++) b1[p * kWX2 + i2w + l * 17] = cplx{re[p][l], im[p][l]};
 #define W_L2(p)                                                                                  \
-    if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int k = 0; k < 8; k++) {                                              \
+    _Pragma("unroll") for (int k = 0; k < 8; k++) {                                              \
         const cplx lo = b1[p * kWX2 + i2r + k];                                                  \
         const cplx hi = b1[p * kWX2 + i2r + k + 8];                                              \
         re[p][k] = fma(K.rg.x, hi.x, fma(-K.rg.y, hi.y, lo.x));                                  \
         im[p][k] = fma(K.rg.x, hi.y, fma(K.rg.y, hi.x, lo.y));                                   \
     }
-#define W_S3(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int k = 0; k < 8; k++) b0[p * kWX2I + i3w + k] = cplx{re[p][k], im[p][k]};
+#define W_S3(p) _Pragma("unroll") for (int k = 0; k < 8; k++) b0[p * kWX2I + i3w + k] = cplx{re[p][k], im[p][k]};
 #define W_L3(p)                                                                                  \
-    if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int l = 0; l < 8; l++) {                                              \
+    _Pragma("unroll") for (int l = 0; l < 8; l++) {                                              \
         const cplx lo = b0[p * kWX2I + i3r + l * 18];                                            \
         const cplx hi = b0[p * kWX2I + i3r + l * 18 + 9];                                        \
         const double dr = fma(K.sig, hi.x, lo.x), di = fma(K.sig, hi.y, lo.y);                   \
         re[p][l] = fma(K.kap[l].x, dr, -(K.kap[l].y * di));                                      \
         im[p][l] = fma(K.kap[l].x, di, K.kap[l].y * dr);                                         \
     }
-#define W_S4(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int m = 0; m < 8; m++) b1[p * kWX1 + i1 + 16 * m] = cplx{re[p][m], im[p][m]};
-#define W_L4(p) if (FHESTR_WIDE_ABLATE != 2) _Pragma("unroll") for (int j = 0; j < 8; j++) { const cplx v = b1[p * kWX1 + j * 128 + t]; re[p][j] = v.x; im[p][j] = v.y; }
+#define W_S4(p) _Pragma("unroll") for (int m = 0; m < 8; m++) b1[p * kWX1 + i1 + 16 * m] = cplx{re[p][m], im[p][m]};
+#define W_L4(p) _Pragma("unroll") for (int j = 0; j < 8; j++) { const cplx v = b1[p * kWX1 + j * 128 + t]; re[p][j] = v.x; im[p][j] = v.y; }
 #define W_ACC(p)                                                                                 \
     {                                                                                            \
         acc_t* acc = c.acc(p);                                                                   \
@@ -403,12 +392,8 @@ FHE_HD void wide_cmux_step_pipe(Ctx& c, acc_t (&a)[2][16], int e, int step, cons
     const cplx* key = c.key_wait(step);
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-#if FHESTR_WIDE_ABLATE == 3
-        const cplx g00 = cplx{1e-9, 2e-9}, g01 = cplx{3e-9, 1e-9}, g10 = cplx{2e-9, 2e-9}, g11 = cplx{1e-9, 4e-9};
-#else
         const cplx g00 = key[wide_key_index(0, 0, u, t)], g01 = key[wide_key_index(0, 1, u, t)];
         const cplx g10 = key[wide_key_index(1, 0, u, t)], g11 = key[wide_key_index(1, 1, u, t)];
-#endif
         const double d0r = re[0][u], d0i = im[0][u], d1r = re[1][u], d1i = im[1][u];
         re[0][u] = fma(d1r, g10.x, fma(-d1i, g10.y, fma(d0r, g00.x, -(d0i * g00.y))));
         im[0][u] = fma(d1r, g10.y, fma(d1i, g10.x, fma(d0r, g00.y, d0i * g00.x)));
