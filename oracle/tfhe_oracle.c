@@ -20,7 +20,10 @@
  * PARITY STATUS: ciphertext-level parity with tfhe-rs is UNPINNED (the reference holds no golden
  * ciphertext, KAT or fixture: SURVEY.md section 8c).  What IS pinned: decrypted plaintext results,
  * against the literal strings of the reference's 43 unit tests (src/main.rs:138-1153) through
- * oracle/string_oracle.py.  This file is the exact-integer ground truth for the engine's
+ * oracle/fhestring_plain.py (tests/golden/reference_tests.json).  What would pin the ciphertext level: the authored Rust
+ * harness integration/fhestr-parity (tfhe 0.5.2) writes key + (input, keyswitched, PBS output) triples that
+ * tests/test_tfhe_rs_fixture.py checks this file and the engine against; it needs a box with cargo.
+ * This file is the exact-integer ground truth for the engine's
  * keyswitch / mod-switch / sample-extract / LUT kernels (bit-exact) and the centre of the
  * tolerance band for the FFT blind rotation.
  *
