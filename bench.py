@@ -54,8 +54,8 @@ WORKLOAD = ("raw batched PBS microbench: 4096 independent 2-bit-message radix bl
 EQ_TABLE = [int((x >> 2) == (x & 3)) for x in range(16)]
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE blind_rotate_kernel launch over 4096 PBS, from the committed
 # ncu --set full capture (cannot be measured inside a bench run: ncu replays kernels ~40 times)
-TRAFFIC_CAPTURE = {"bytes": 170.1e6, "file": "profiles/r2b_blind_rotate_ncu_full.csv (ncu --set full, scripts/r2b_profiles_gpu.sh)",
-                   "note": "99.5 MB read + 70.6 MB written; algorithmic 140.0 MB (24.3 MB keyswitched inputs + 67.1 MB "
+TRAFFIC_CAPTURE = {"bytes": 180.7e6, "file": "profiles/r2b_blind_rotate_ncu_full.csv (ncu --set full, scripts/r2b_profiles_gpu.sh)",
+                   "note": "106.6 MB read + 74.1 MB written; algorithmic 140.0 MB (24.3 MB keyswitched inputs + 67.1 MB "
                            "outputs + 48.6 MB Fourier BSK once)"}
 
 

@@ -5,9 +5,9 @@
 // per SM (launch bound 4: ptxas may use 255 registers per thread, the rolled step needs 168 and spends the rest on
 // loads in flight).
 // Shared memory per pair: the mod-switched mask (2 KiB), the accumulator 2 x 2048 words on the 32-bit torus (16 KiB,
-// each polynomial on an 8 KiB-aligned shared address: 5 KiB of padding behind the mask) and one padded transpose
-// matrix per warp (2 x 8448 B) = 40 448 B: 4 CTAs (+ 1 KiB reserved each) still fit the 164 KB carve-out, which
-// leaves 92 KB of L1 for the BSK tile the 4 CTAs of an SM read at nearly the same time.
+// each polynomial on an 8 KiB-aligned shared address: 4 KiB of padding behind the mask) and one padded transpose
+// matrix of complex words per warp (2 x 16 896 B) = 56 320 B: 4 CTAs (+ 1 KiB reserved each) take 224 of the SM's
+// 228 KB (carve-out 100 %: since the twiddles left for tensor memory the L1 served 11 % of the loads).
 // Tensor memory per CTA: 128 columns (4 CTAs = the SM's 512).  Warp w owns TMEM lanes 32 w .. 32 w + 31; thread t keeps
 // its 32 inter-pass twiddles tf[k1*32 + t] (128 words) in the 128 columns of its lane: written once per PBS with
 // tcgen05.st, read 8 twiddles at a time with tcgen05.ld (SASS STTM / LDTM) -- a lane-private scratch file next to the
@@ -21,14 +21,16 @@ namespace fhestr {
 constexpr int kAtildeBytes = 2048;  // up to 1024 u16
 constexpr int kAccBytes = 2 * kN * (int)sizeof(acc_t);  // 16 KiB: both polynomials on the 32-bit torus
 // layout: [two transpose matrices][mask 2 KiB][pad][acc0 8 KiB | acc1 8 KiB, each on an 8 KiB-aligned SHARED address].
-// The CTA's shared window starts at 0x400 (1 KiB is reserved per CTA), so the pad is 5 KiB: 40 448 B per CTA, and
-// 4 x (40 448 + 1 024) = 162 KiB still fits the 164 KiB carve-out.  The kernel computes the pad from the real
-// address and traps if the dynamic allocation is too small for it.
+// The CTA's shared window starts at 0x400 (1 KiB is reserved per CTA), so the pad is 4 KiB: 56 320 B per CTA, and
+// 4 x (56 320 + 1 024) = 224 KiB of the SM's 228.  The kernel computes the pad from the real address and traps if the
+// dynamic allocation is too small for it.
 constexpr int kSharedBase = 0x400;
+constexpr int kCtasPerSmForSmem = 4;
 constexpr int kXbufBytes = 2 * kWarpXbufDoubles * 8;   // one padded matrix per warp
 constexpr int kFrontBytes = kXbufBytes + kAtildeBytes;
 constexpr int kPadBytes = (8192 - ((kSharedBase + kFrontBytes) & 8191)) & 8191;
-constexpr int kSmemBytes = kFrontBytes + kPadBytes + kAccBytes;  // 39 936 B
+constexpr int kSmemBytes = kFrontBytes + kPadBytes + kAccBytes;  // 56 320 B
+static_assert(kCtasPerSmForSmem * (kSmemBytes + 1024) <= 228 * 1024, "four CTAs per SM");
 constexpr int kCtasPerSm = 4;
 constexpr int kTmemCols = 128;   // = words of a lane's twiddle set; 4 CTAs per SM use all 512 columns
 static_assert(kCtasPerSm * kTmemCols <= 512, "tensor memory of one SM");
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(64, kCtasPerSm) blind_rotate_kernel(BrBatchArg
 }
 
 cudaError_t blind_rotate_configure() {
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 

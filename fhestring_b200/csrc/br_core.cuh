@@ -16,7 +16,7 @@
 //   twiddle Tf(k1,n2) = exp(i pi n2 (1-4 k1)/N), transpose through shared memory
 //   pass 2 (lane = k1, registers n2 -> k2): plain DFT-32               (fft32_dft)
 // ONE WARP owns one polynomial: 32 complex points per lane live in registers, the only exchange inside
-// a transform is one 32x32 transpose (real and imaginary parts through one 8.25 KB padded buffer), and
+// a transform is one 32x32 transpose of complex words through a 16.5 KB padded buffer, and
 // only __syncwarp is needed.  The two warps of a PBS (mask polynomial, body polynomial) swap one
 // spectrum per step through the same buffers (pair barrier).
 //
@@ -40,11 +40,11 @@
 
 // Compile-time knobs of the step (A/B-measured on one B200, profiles/r2_compact_tmem.md; build.py --variant builds any
 // other setting as a second library for FHESTR_ENGINE_LIB):
-//   FHESTR_BR_PREFETCH = key rows per half-step requested ahead of the pair barrier (8 = 64 registers)
+//   FHESTR_BR_PREFETCH = key rows per half-step requested ahead of the pair barrier (6 = 48 registers)
 //   FHESTR_BR_CVT_FP64 = m > 0: every m-th torus conversion of the epilogue runs on the FP64 pipe (four FP64
 //       instructions, bit-identical to the F2I) instead of the conversion unit; 0 = none (round 1's kernel: 4)
 #ifndef FHESTR_BR_PREFETCH
-#define FHESTR_BR_PREFETCH 8
+#define FHESTR_BR_PREFETCH 6
 #endif
 #ifndef FHESTR_BR_CVT_FP64
 #define FHESTR_BR_CVT_FP64 0
@@ -57,9 +57,9 @@ typedef long long i64;
 
 constexpr int kN = 2048;          // polynomial size
 constexpr int kM = 1024;          // complex points
-constexpr int kXPad = 33;         // transpose row stride (doubles): conflict-free 64-bit column reads
-constexpr int kXbufDoubles = 32 * kXPad;  // 1056 doubles = 8448 B: one padded 32 x 32 matrix
-constexpr int kWarpXbufDoubles = kXbufDoubles;  // per warp: ONE matrix (shared-memory carve-out 164 KB instead of 228 KB: 92 KB of L1 for the BSK tile)
+constexpr int kXPad = 33;         // transpose row stride (complex words): conflict-free 128-bit column reads
+constexpr int kXbufDoubles = 32 * kXPad;  // 1056 words
+constexpr int kWarpXbufDoubles = 2 * kXbufDoubles;  // per warp: ONE matrix of 32 x 33 complex words = 16 896 B
 constexpr int kPbsBaseLog = 23;
 constexpr int kBskPrefetch = FHESTR_BR_PREFETCH;
 constexpr int kTwChunks = 4;      // a lane's 32 twiddles = 128 words are read 8 twiddles (32 words) at a time
@@ -143,22 +143,20 @@ FHE_HD acc_t torus32_conv(double x, int idx) {
 #define FHESTR_TWIST(i) kFft32TwistHost[i]
 #endif
 
-// 32x32 transpose of one double per (lane, register) through the warp's padded buffer, real parts then imaginary
-template <class Ctx>
-FHE_HD void transpose32_half(Ctx& c, double (&v)[32]) {
-    const int t = c.lane();
-    double* buf = c.xbuf();
-#pragma unroll
-    for (int r = 0; r < 32; r++) buf[r * kXPad + t] = v[r];
-    c.syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; r++) v[r] = buf[t * kXPad + r];
-    c.syncwarp();
-}
+// 32x32 transpose of one complex point per (lane, register) through the warp's padded buffer: 16-byte words, row stride
+// 33 words, so both the row-wise stores and the column-wise loads are conflict-free per quarter-warp.  (Up to the first
+// half of round 2 the real and imaginary parts went through an 8.25 KB matrix one after the other: twice the
+// shared-memory instructions and warp barriers for the same wavefronts; 43.27 -> 42.88 ms per 4096 PBS.)
 template <class Ctx>
 FHE_HD void transpose32(Ctx& c, double (&re)[32], double (&im)[32]) {
-    transpose32_half(c, re);
-    transpose32_half(c, im);
+    const int t = c.lane();
+    cplx* buf = reinterpret_cast<cplx*>(c.xbuf());
+#pragma unroll
+    for (int r = 0; r < 32; r++) buf[r * kXPad + t] = cplx{re[r], im[r]};
+    c.syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; r++) { const cplx v = buf[t * kXPad + r]; re[r] = v.x; im[r] = v.y; }
+    c.syncwarp();
 }
 
 // Multiply the 32 points of this lane by its inter-pass twiddles tf[r*32 + lane], r = 0..31.  The words come from the
@@ -237,8 +235,9 @@ FHE_HD void cmux_step(Ctx& c, acc_t (&a)[64], int e, const cplx* g, const cplx* 
             transpose32(c, A, B);
             twiddle32(c, A, B, tf, w0);
         } else if (it == 1) {
-            // Fourier-domain GGSW product.  The two warps swap their spectra through the transpose buffers (16
-            // spectrum rows at a time: a buffer holds 528 complex points) and each forms ITS output polynomial completely:
+            // Fourier-domain GGSW product.  The two warps swap their spectra through the transpose buffers, 16 spectrum
+            // rows at a time (the second half's key rows are requested while the first half multiplies), and each
+            // forms ITS output polynomial completely:
             //     out_p = D_p * G[p][p] + D_(1-p) * G[1-p][p]
             // the second product accumulates with FMAs, so the step costs 8 FP64 operations per point instead of 10
             cplx* xo = reinterpret_cast<cplx*>(c.xbuf());

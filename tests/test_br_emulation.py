@@ -13,7 +13,7 @@ from conftest import ROOT, monomial_mul
 
 # every build of the thread program: the default kernel and the settings of its two compile-time knobs (br_core.cuh)
 VARIANTS = {
-    "default": (),                                        # no torus conversion on the FP64 pipe, 8 key rows prefetched
+    "default": (),                                        # no torus conversion on the FP64 pipe, 6 key rows prefetched
     "fp64_conversions": ("FHESTR_BR_CVT_FP64=1",),        # every torus conversion by the 1.5 * 2^52 trick
     "every_4th_fp64_depth_12": ("FHESTR_BR_CVT_FP64=4", "FHESTR_BR_PREFETCH=12"),
 }
