@@ -281,15 +281,17 @@ def query_leg(ctx, name, method, vals, steps):
     prog.close()
     g.close()
 
-    # the call a user makes: MyServerKey.<method>(...) then the download (record + compile + bind + upload + run + D2H)
+    # the call a user makes: MyServerKey.<method>(...) then the download (record + compile + bind + upload + run + D2H);
+    # the chars are views of the PINNED input buffer (the e2e contract's host memory), string by string as they lie
     sk = ctx["sk"]
+    cts_pinned = cts.numpy().view(np.uint64)
     api = []
     api_got = None
     for _ in range(2 if info.n_pbs >= 50_000 else 3):
         sk.reset()
         off, args = 0, []
         for i, v in enumerate(vals):
-            chars = [FheAsciiChar(ct=cts_np[4 * (off + j):4 * (off + j + 1)]) for j in range(len(v))]
+            chars = [FheAsciiChar(ct=cts_pinned[4 * (off + j):4 * (off + j + 1)]) for j in range(len(v))]
             args.append(FheString(chars) if i == 0 or method in ("eq", "ge", "le") else chars)
             off += len(v)
         barrier()

@@ -226,6 +226,28 @@ class MyServerKey:
         c.sk, c.id, c.graph = self, int(ids[0]), self.graph
         return c.id
 
+    def _contiguous_run(self, chars):
+        """[4 len(chars)][N+1] view over the chars' ciphertexts when they lie back to back in memory, else None"""
+        big = self.engine.big
+        first = chars[0].ct
+        if not (isinstance(first, np.ndarray) and first.dtype == np.uint64 and first.flags.c_contiguous and first.shape == (4, big)):
+            return None
+        step = 4 * big * 8
+        p0 = first.__array_interface__["data"][0]
+        for i, c in enumerate(chars):
+            a = c.ct
+            if not (isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags.c_contiguous and a.shape == (4, big)
+                    and a.__array_interface__["data"][0] == p0 + i * step):
+                return None
+        owner = first
+        while isinstance(owner.base, np.ndarray):
+            owner = owner.base
+        lo = owner.__array_interface__["data"][0]
+        if owner.dtype != np.uint64 or not owner.flags.c_contiguous or p0 < lo or p0 + len(chars) * step > lo + owner.nbytes:
+            return None
+        k = (p0 - lo) // 8
+        return owner.reshape(-1)[k:k + len(chars) * 4 * big].reshape(-1, big)
+
     def _adopt_all(self, chars):
         chars = list(chars)
         fresh = [c for c in chars if not self._mine(c)]
@@ -234,11 +256,16 @@ class MyServerKey:
                              "and has no host ciphertext to re-upload")
         if fresh:
             ids, slots = self.graph.input_chars(len(fresh))
-            cts = np.stack([c.ct for c in fresh]).reshape(-1, self.engine.big)
             flat = slots.reshape(-1)
             # input slots are handed out consecutively: one upload
             assert (np.diff(flat.astype(np.int64)) == 1).all()
-            self.engine.upload(int(flat[0]), cts)
+            run = self._contiguous_run(fresh)
+            if run is not None:
+                # the chars are consecutive views of one buffer (what MyClientKey.encrypt and any caller that keeps a
+                # string's ciphertexts together hand over): upload it as it lies, no gathering copy on the host
+                self.engine.upload(int(flat[0]), run)
+            else:
+                self.engine.upload(int(flat[0]), np.stack([c.ct for c in fresh]).reshape(-1, self.engine.big))
             for c, i in zip(fresh, ids):
                 c.sk, c.id, c.graph = self, int(i), self.graph
         return np.array([c.id for c in chars], np.uint32)
