@@ -26,7 +26,7 @@ BlockId Graph::trivial_block(int value) {
     value = mod32(value);
     if (!triv_cache_init) {
         nodes.reserve(1 << 16);
-        cse.reserve(1 << 16);
+        cse_tab.assign(1 << 14, ~0ull);
         for (int v = 0; v < 32; v++) {
             BlockNode n;
             n.kind = BKind::Trivial;
@@ -242,13 +242,9 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     if (terms.empty()) return trivial_block(half ? (c < 16 ? (table[c] & 0x7f) : 1 - (int)(table[c - 16] & 0x7f)) : table[c & 15] * (c < 16 ? 1 : -1));
 
     const int lid = lut_id(table);
-    std::string key;
-    key.reserve(16 + terms.size() * 8);
-    key.append(reinterpret_cast<const char*>(&lid), 4);
-    key.append(reinterpret_cast<const char*>(&c), 4);
-    for (auto& t : terms) key.append(reinterpret_cast<const char*>(&t), sizeof(Term));
-    auto it = cse.find(key);
-    if (it != cse.end()) return it->second;
+    const uint64_t key = cse_hash(lid, c, terms);
+    const BlockId hit = cse_find(key, lid, c, terms);
+    if (hit != kNoBlock) return hit;
 
     BlockNode n;
     n.kind = BKind::Pbs;
@@ -261,8 +257,57 @@ BlockId Graph::pbs(const std::vector<std::pair<BlockId, int>>& ops_in, int cst, 
     nodes.push_back(n);
     n_pbs_nodes++;
     const BlockId id = (BlockId)nodes.size() - 1;
-    cse[key] = id;
+    cse_insert(key, id);
     return id;
+}
+
+uint64_t Graph::cse_hash(int lut, int cst, const std::vector<Term>& terms) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ ((uint64_t)(uint32_t)lut << 32 | (uint32_t)cst);
+    for (const Term& t : terms) {
+        h ^= ((uint64_t)t.blk << 32) | (uint32_t)t.coeff;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 29;
+    }
+    h *= 0xc4ceb9fe1a85ec53ull;
+    return h ^ (h >> 32);
+}
+
+static constexpr uint64_t kCseEmpty = ~0ull;
+
+BlockId Graph::cse_find(uint64_t h, int lut, int cst, const std::vector<Term>& terms) const {
+    if (cse_tab.empty()) return kNoBlock;
+    const size_t mask = cse_tab.size() - 1;
+    const uint64_t tag = h & 0xffffffffull;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+        const uint64_t e = cse_tab[i];
+        if (e == kCseEmpty) return kNoBlock;
+        if ((e >> 32) != tag) continue;                 // the node is only touched when the stored hash half matches
+        const BlockNode& n = nodes[(BlockId)e];
+        if (n.lut == lut && n.cst == cst && n.terms.size() == terms.size() &&
+            std::equal(terms.begin(), terms.end(), n.terms.begin(), [](const Term& a, const Term& b) { return a.blk == b.blk && a.coeff == b.coeff; }))
+            return (BlockId)e;
+    }
+}
+
+void Graph::cse_insert(uint64_t h, BlockId id) {
+    if (cse_tab.empty()) cse_tab.assign(1 << 14, kCseEmpty);
+    if (2 * (cse_count + 1) > cse_tab.size()) {   // keep the load below one half; an entry keeps the LOWER hash half,
+        std::vector<uint64_t> old;                 // which is all a slot index needs: growing touches no node
+        old.swap(cse_tab);
+        cse_tab.assign(old.size() * 4, kCseEmpty);
+        const size_t mask = cse_tab.size() - 1;
+        for (uint64_t e : old) {
+            if (e == kCseEmpty) continue;
+            size_t i = (size_t)(e >> 32) & mask;
+            while (cse_tab[i] != kCseEmpty) i = (i + 1) & mask;
+            cse_tab[i] = e;
+        }
+    }
+    const size_t mask = cse_tab.size() - 1;
+    size_t i = (size_t)h & mask;
+    while (cse_tab[i] != kCseEmpty) i = (i + 1) & mask;
+    cse_tab[i] = (h << 32) | id;
+    cse_count++;
 }
 
 // f(x, y) over clean 2-bit block values; one operand trivial -> univariate LUT on the other

@@ -30,6 +30,7 @@
 namespace fhestr {
 
 typedef uint32_t BlockId;
+constexpr BlockId kNoBlock = 0xffffffffu;
 typedef std::array<BlockId, 4> Char;  // little-endian base-4 digits of a u8
 
 struct Term {
@@ -145,7 +146,14 @@ private:
     std::vector<BlockId> outputs;
     std::vector<std::array<uint8_t, 16>> lut_tables;
     std::map<std::array<uint8_t, 16>, int> lut_ids;
-    std::unordered_map<std::string, BlockId> cse;
+    // common-subexpression table of the PBS nodes: open addressing over node ids, keyed by a hash of (lut, constant,
+    // terms) and compared against the node itself -- no key strings (they were 40 % of the recording time of a
+    // 138 k-PBS graph)
+    std::vector<uint64_t> cse_tab;   // (lower hash half << 32) | node id; all ones = free
+    size_t cse_count = 0;
+    static uint64_t cse_hash(int lut, int cst, const std::vector<Term>& terms);
+    BlockId cse_find(uint64_t h, int lut, int cst, const std::vector<Term>& terms) const;
+    void cse_insert(uint64_t h, BlockId id);
     BlockId triv_cache[32];
     bool triv_cache_init = false;
     uint64_t n_pbs_nodes = 0;
