@@ -937,6 +937,11 @@ bool Graph::compile(CompiledProgram& out, std::string& err, uint32_t slot_align)
         return true;
     };
     out.level_offsets.push_back(0);
+    {
+        size_t n_jobs = 0;
+        for (int l = 0; l <= depth; l++) n_jobs += pbs_at[l].size() + lin_at[l].size();
+        out.jobs.reserve(n_jobs);
+    }
     for (int l = 0; l <= depth; l++) {
         if (pbs_at[l].empty() && lin_at[l].empty()) continue;
         out.level_first_dst.push_back(pbs_at[l].empty() ? 0u : (uint32_t)nodes[pbs_at[l][0]].slot);
