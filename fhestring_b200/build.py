@@ -25,7 +25,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple[str, ...] = ()) -> str:
-    """variant="tag" with defines=("NAME=VALUE", ...) builds an experimental kernel variant (the FHESTR_BR_* switches
+    """variant="tag" with defines=("NAME=VALUE", ...) builds an experimental kernel variant (the FHESTR_BR_PREFETCH / FHESTR_BR_CVT_FP64 knobs
     of br_core.cuh) as libfhestr_engine_<tag>.so next to the default library; select it with FHESTR_ENGINE_LIB for
     A/B runs (scripts/ab_variants_gpu.sh)."""
     objdir = os.path.join(HERE, f"build_{variant}" if variant else "build")

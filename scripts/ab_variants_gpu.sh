@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of blind-rotation kernel variants on ONE GPU box (how profiles/r1_final2_ab_variants.md was measured).
-#   here:        python fhestring_b200/build.py --variant slim_cvt3 FHESTR_BR_SLIM=1 FHESTR_BR_CVT_FP64=3   (per variant)
-#   on the box:  gpurun -- 'bash scripts/ab_variants_gpu.sh default slim_cvt3 ...'
+#   here:        python fhestring_b200/build.py --variant p8_cvt4 FHESTR_BR_PREFETCH=8 FHESTR_BR_CVT_FP64=4   (per variant)
+#   on the box:  gpurun -- 'bash scripts/ab_variants_gpu.sh default p8_cvt4 ...'
 # Each tag runs the short PBS bench (about 7 s) against fhestring_b200/libfhestr_engine_<tag>.so ("default" is the
 # shipped library); the fastest verified one then runs the whole GPU suite.  Every step has its own timeout.
 # Outputs: gpurun_out/ab_<tag>.json, gpurun_out/ab_winner.txt, gpurun_out/ab_pytest_winner.log
