@@ -451,6 +451,23 @@ static int launch_wide(const fhestr_engine* e, const BrBatchArgs& br, uint32_t n
            launch_blind_rotate_wide(br_slice(br, 2 * sms, n_pbs - 2 * sms), e->stream);
 }
 
+// Blind rotation of one level.  Above three jobs per SM the throughput kernel runs it in waves of four PBS per SM; a last
+// wave that is mostly empty still costs a whole PBS chain on that kernel (626 jobs = one wave + 34: 9.95 ms), so a
+// small remainder goes to the latency kernel instead, right behind the full waves (8.85 ms).  Measured on one B200
+// (profiles/r2b_tail_remainder.md): a remainder of at most one job per SM pays up to three full waves (1332 jobs: 16.1
+// -> 15.1 ms; from four waves on the CTAs of a launch have drifted apart enough to hide their own tail), a remainder of
+// up to three jobs per SM only behind a single full wave (950 jobs: 12.7 -> 12.4 ms).
+static int launch_level_br(const fhestr_engine* e, const BrBatchArgs& br, uint32_t n_pbs) {
+    if (use_wide(e, n_pbs)) return launch_wide(e, br, n_pbs);
+    if (e->br_mode == 0) {
+        const uint32_t sms = (uint32_t)e->n_sms, wave = 4 * sms;
+        const uint32_t full = n_pbs / wave, r = n_pbs % wave;
+        if (r > 0 && ((full >= 1 && full <= 3 && r <= sms) || (full == 1 && r <= 3 * sms)))
+            return launch_blind_rotate(br_slice(br, 0, n_pbs - r), e->stream) + launch_wide(e, br_slice(br, n_pbs - r, r), r);
+    }
+    return launch_blind_rotate(br, e->stream);
+}
+
 // launch one level: jobs[0, n_pbs) are PBS jobs, jobs[n_pbs, n_all) leveled-only
 static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs, uint32_t n_all, bool peer_stores = false) {
     if (n_pbs) {
@@ -474,7 +491,7 @@ static int run_level(fhestr_engine* e, const fhestr_job* d_jobs, uint32_t n_pbs,
         if (e->peers_attached && peer_stores) {
             for (uint32_t r = 0; r < e->world; r++) if (r != e->rank) br.peer_arena[br.n_peers++] = e->peer_arena[r];
         }
-        e->launches += use_wide(e, n_pbs) ? launch_wide(e, br, n_pbs) : launch_blind_rotate(br, e->stream);
+        e->launches += launch_level_br(e, br, n_pbs);
         if (e->timing) { CK(cudaEventRecord(t.c, e->stream)); e->timed.push_back(t); }
     }
     if (n_all > n_pbs) e->launches += launch_linear(d_jobs + n_pbs, (int)(n_all - n_pbs), e->arena, e->stream);
@@ -768,7 +785,7 @@ int fhestr_debug_blind_rotate(fhestr_engine* e, const uint64_t* ks_host, const i
     br.bsk = e->bsk_f; br.tf = e->tf; br.init_acc = d_init; br.out_acc = d_out;
     br.n = e->prm.n; br.B = (int)count;
     br.bsk_w = e->bsk_w; br.wide_tab = e->wide_tab;
-    e->launches += use_wide(e, count) ? launch_wide(e, br, count) : launch_blind_rotate(br, e->stream);
+    e->launches += launch_level_br(e, br, count);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc_out_host, d_out, acc_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
