@@ -356,6 +356,34 @@ def test_full_parameters_latency_kernel(full_engine, full_oracle):
     assert np.abs(dp).max() < 2.0**-11
 
 
+def test_level_remainder_runs_on_the_latency_kernel(full_engine, full_oracle):
+    """a level of one to three full waves of four PBS per SM plus a small remainder: the full waves run on the throughput
+    kernel, the remainder on the latency kernel (engine.cu: launch_level_br) -- every block decrypts right, the first
+    blocks are word for word what the throughput kernel alone produces and the remainder what the latency kernel produces"""
+    import torch
+    from fhestring_b200.engine import single_term_jobs
+    o, keys = full_oracle
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    wave = 4 * sms
+    table = [(5 * x + 3) % 16 for x in range(16)]
+    lid = full_engine.lut(table)
+    for B, r in ((wave + 34, 34), (wave + 3 * sms - 5, 3 * sms - 5), (2 * wave + sms, sms)):
+        rng = np.random.default_rng(B)
+        vals = rng.integers(0, 16, B)
+        full_engine.upload(0, o.encrypt_big(keys, vals, seed=B))
+        jobs = single_term_jobs(4096 + np.arange(B), np.arange(B), lid)
+        outs = {}
+        for mode in (0, 1, 2):
+            full_engine.set_br_mode(mode)
+            full_engine.pbs_batch(jobs if mode != 2 else jobs[B - r:])
+            outs[mode] = full_engine.download(4096, B)
+        full_engine.set_br_mode(0)
+        want = np.array([table[v] for v in vals])
+        assert np.array_equal(o.decrypt_big(keys, outs[0]), want), B
+        assert np.array_equal(outs[0][:B - r], outs[1][:B - r]), B     # full waves: the throughput kernel's words
+        assert np.array_equal(outs[0][B - r:], outs[2][B - r:]), B     # remainder: the latency kernel's words
+
+
 def test_full_parameters_phase_close_to_cpu_fft_route(full_engine, full_oracle):
     """same 8 inputs through the oracle's f64 route and the GPU: identical decryption, and the two
     output phases differ by no more than the scheme's own rounding noise (both are valid PBS)"""
