@@ -241,7 +241,9 @@ int fhestr_measure_fp64_peak(fhestr_engine* e, double* tflops, double* sm_clock_
 uint64_t fhestr_kernel_launches(const fhestr_engine* e);
 /* Which blind-rotation kernel runs a level.  mode 0 (default): by level size -- levels of at most wide_max_jobs PBS
  * jobs (0 = three times the SM count) run on the latency kernel, larger ones on the throughput kernel (four PBS per
- * SM, one pair of warps each).  The latency kernel has two forms, also picked by size: ONE PBS per SM over 128 threads
+ * SM, one pair of warps each) in waves of four jobs per SM, with a small last-wave remainder handed to the latency
+ * kernel behind the full waves (at most one job per SM behind one to three waves, up to three per SM behind a single
+ * one).  The latency kernel has two forms, also picked by size: ONE PBS per SM over 128 threads
  * with a two-tile key ring fed by bulk TMA (up to one job per SM), and TWO PBS per SM over 256 threads sharing one
  * key tile (above).  mode 1 forces the throughput kernel, 2 the latency kernel (form by size), 3 / 4 its single /
  * pair form (tests, measurements).  All kernels compute the same function; their outputs are different valid
