@@ -287,7 +287,7 @@ def query_leg(ctx, name, method, vals, steps):
     cts_pinned = cts.numpy().view(np.uint64)
     api = []
     api_got = None
-    for _ in range(2 if info.n_pbs >= 50_000 else 3):
+    for _ in range(2 if info.n_pbs >= 50_000 else 4):
         sk.reset()
         off, args = 0, []
         for i, v in enumerate(vals):
@@ -303,12 +303,18 @@ def query_leg(ctx, name, method, vals, steps):
         d = ck.decrypt_u8(raw)
         api_got = bytes(d).split(b"\0")[0].decode("ascii", "replace") if is_str else int(d[0])
     barrier()
-    t = torch.tensor([float(np.median(dev)), float(np.median(e2e)), float(np.min(api))], device="cuda", dtype=torch.float64)
+    # the first call of a query shape records, compiles and binds it; the later ones hit MyServerKey's plan cache
+    api_first, api_cached = float(api[0]), float(np.min(api[1:])) if len(api) > 1 else float(api[0])
+    t = torch.tensor([float(np.median(dev)), float(np.median(e2e)), api_cached, api_first], device="cuda", dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     show = (lambda x: x if not isinstance(x, str) or len(x) <= 48 else x[:45] + "...")
     return {"latency_ms": float(t[0]), "e2e_latency_ms": float(t[1]), "api_latency_ms": float(t[2]),
+            "api_first_call_ms": float(t[3]),
+            "api_how": "MyServerKey.<method>(...) + download, host wall clock: api_first_call_ms = the first call of this query "
+                       "shape (record + compile + bind + upload + run + D2H), api_latency_ms = the best later call on the "
+                       "same shape (plan cache: upload + run of the bound program + D2H)",
             "levels": int(info.n_levels), "pbs": int(info.n_pbs), "level_pbs": [int(x) for x in npbs],
             "decrypted": show(got), "expected": show(want), "verified": bool(got == want and api_got == want),
             "h2d_bytes": int(n_in * eng.big * 8), "d2h_bytes": int(len(res_slots) * eng.big * 8),

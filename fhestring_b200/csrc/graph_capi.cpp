@@ -268,6 +268,12 @@ int fhestr_graph_char_slots(const fhestr_graph* g, const uint32_t* ids, uint32_t
     return FHESTR_OK;
 }
 
+int fhestr_graph_reserve_slots(fhestr_graph* g, uint32_t first_free) {
+    if (!g) return FHESTR_E_INVALID;
+    g->g.reserve_slots(first_free);
+    return FHESTR_OK;
+}
+
 static int graph_bind_impl(fhestr_graph* g, fhestr_engine* e, fhestr_program** out) {
     if (!g || !e || !out) return FHESTR_E_INVALID;
     if (!g->compiled) return gfail(g, FHESTR_E_STATE, "graph not compiled");

@@ -39,12 +39,13 @@ class FheAsciiChar:
     """One encrypted u8 = 4 radix blocks.  Either a fresh host ciphertext (`ct`, from the client) or a value
     of a server key's graph (`sk`, `id`), or both once a fresh ciphertext has been handed to a server key."""
 
-    __slots__ = ("ct", "sk", "id", "graph")
+    __slots__ = ("ct", "sk", "id", "graph", "slots")
 
-    def __init__(self, ct=None, sk=None, id=None, graph=None):
+    def __init__(self, ct=None, sk=None, id=None, graph=None, slots=None):
         # `graph` is the Graph instance `id` belongs to: MyServerKey.reset() starts a new graph, and an id of the
-        # old one must never be used in the new one (it would name an unrelated node)
-        self.ct, self.sk, self.id, self.graph = ct, sk, id, graph
+        # old one must never be used in the new one (it would name an unrelated node).  `slots`: the four arena blocks
+        # of a result computed by a cached plan (MyServerKey._run_plan): a value of `graph`'s lifetime without a node
+        self.ct, self.sk, self.id, self.graph, self.slots = ct, sk, id, graph, slots
 
     @staticmethod
     def encrypt_trivial(value: int, public_parameters, server_key: "MyServerKey") -> "FheAsciiChar":  # :17-25
@@ -204,19 +205,40 @@ class MyServerKey:
         self.key = self  # the reference passes `&my_server_key.key` around (main.rs:146)
         self.graph = Graph()
         self.last_info = None
+        # plan cache: a string method called on fresh host ciphertexts right after reset() is recorded, compiled and
+        # bound ONCE per (method, argument lengths, clear n, recording, world); the same call on new inputs re-runs
+        # the bound program (upload, run) without recording anything.  plan_cache = False: always record.
+        self.plan_cache = True
+        self._plans = {}
+        self._fresh = True
+        self.plan_hits = 0
 
     def reset(self):
         """drop everything recorded and reuse the arena from slot 0 (one query = one graph)"""
         self.graph.close()
         self.graph = Graph()
+        self._fresh = True
 
     # ---- plumbing between host ciphertexts, graph ids and the arena
     def _mine(self, c: FheAsciiChar) -> bool:
         return c.id is not None and c.sk is self and c.graph is self.graph
 
+    def _plan_value(self, c: FheAsciiChar) -> bool:
+        return c.slots is not None and c.sk is self and c.graph is self.graph
+
+    def _materialise(self, chars):
+        """results of a cached plan that are used as operands: fetch their ciphertexts, they re-enter as inputs"""
+        need = [c for c in chars if c.ct is None and self._plan_value(c)]
+        if need:
+            got = self.engine.download_slots(np.concatenate([c.slots for c in need]).astype(np.int64)).reshape(len(need), 4, self.engine.big)
+            for c, g in zip(need, got):
+                c.ct = g
+
     def _adopt(self, c: FheAsciiChar) -> int:
         if self._mine(c):
             return c.id
+        self._fresh = False
+        self._materialise([c])
         if c.ct is None:
             raise ValueError("this FheAsciiChar is a value of another server key, or of this one before reset(), "
                              "and has no host ciphertext to re-upload")
@@ -251,6 +273,8 @@ class MyServerKey:
     def _adopt_all(self, chars):
         chars = list(chars)
         fresh = [c for c in chars if not self._mine(c)]
+        self._fresh = False
+        self._materialise(fresh)
         if any(c.ct is None for c in fresh):
             raise ValueError("an FheAsciiChar is a value of another server key, or of this one before reset(), "
                              "and has no host ciphertext to re-upload")
@@ -274,6 +298,7 @@ class MyServerKey:
         return FheAsciiChar(sk=self, id=int(cid), graph=self.graph)
 
     def _trivial(self, value: int) -> FheAsciiChar:
+        self._fresh = False
         return self._wrap(self.graph.trivial_chars([value & 255])[0])
 
     def _char_op(self, op, a, b=None, c=None) -> FheAsciiChar:
@@ -282,6 +307,9 @@ class MyServerKey:
 
     def flush(self, outputs):
         """compile and run everything `outputs` depend on"""
+        outputs = [c for c in outputs if not self._plan_value(c)]     # results of a cached plan exist already
+        if not outputs:
+            return
         if not all(self._mine(c) for c in outputs):
             raise ValueError("flush() of a char that is not a value of this server key's current graph")
         ids = np.array([c.id for c in outputs], np.uint32)
@@ -292,8 +320,15 @@ class MyServerKey:
         self.graph.execute(self.engine, self.rank, self.world)
 
     def _download(self, chars) -> np.ndarray:
+        chars = list(chars)
         self.flush(chars)
-        slots = self.graph.char_slots(np.array([c.id for c in chars], np.uint32))
+        slots = np.zeros((len(chars), 4), np.uint32)
+        rec = [i for i, c in enumerate(chars) if not self._plan_value(c)]
+        if rec:
+            slots[rec] = self.graph.char_slots(np.array([chars[i].id for i in rec], np.uint32))
+        for i, c in enumerate(chars):
+            if self._plan_value(c):
+                slots[i] = c.slots
         flat = slots.reshape(-1).astype(np.int64)
         if len(flat) and (np.diff(flat) == 1).all():
             out = self.engine.download(int(flat[0]), len(flat))
@@ -306,11 +341,65 @@ class MyServerKey:
         chars = a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else list(a))
         return self._adopt_all(chars) if chars else np.zeros(0, np.uint32)
 
+    def _arg_chars(self, a):
+        return a.bytes if isinstance(a, FheString) else ([a] if isinstance(a, FheAsciiChar) else list(a))
+
     def _str(self, method, *args, clear_n=0):
+        key = None
+        if self.plan_cache and self._fresh:
+            lists = [self._arg_chars(a) for a in args]
+            if all(len(l) for l in lists) and all(c.ct is not None and not self._mine(c) and not self._plan_value(c) for l in lists for c in l):
+                key = (method, tuple(len(l) for l in lists), bool(self.fast), int(clear_n), int(self.world))
+                plan = self._plans.get(key)
+                if plan is not None:
+                    return self._run_plan(plan, lists)
         ids = [self._ids(a) for a in args]
         rs, rc = self.graph.string_op(method, ids, fast=self.fast, clear_n=clear_n)
         s = None if rs is None else FheString([self._wrap(i) for i in rs])
         c = None if rc is None else self._wrap(rc)
+        if key is not None:
+            self._make_plan(key, ids, s, c)
+        return s, c
+
+    def _make_plan(self, key, ids, s, c):
+        """first call of a query shape: compute its results now (compile, bind, run, commit) and keep the bound program"""
+        outs = (list(s.bytes) if s is not None else []) + ([c] if c is not None else [])
+        oid = np.array([x.id for x in outs], np.uint32)
+        self.graph.mark_output(oid)
+        self.last_info = info = self.graph.compile(self.world)
+        if info.slots_used > self.engine.arena_blocks:
+            raise MemoryError(f"graph needs {info.slots_used} arena blocks, engine has {self.engine.arena_blocks}")
+        prog = self.graph.bind(self.engine)
+        triv = self.graph.trivials()
+        prog.run(rank=self.rank, world=self.world)
+        self.engine.sync()           # a failed run (peer barrier time-out) surfaces here, before anything is committed or cached
+        self.graph.commit()
+        oslots = self.graph.char_slots(oid)
+        self._plans[key] = dict(
+            prog=prog, in_first=[int(self.graph.char_slots(i[:1])[0, 0]) for i in ids], n_slots=int(info.slots_used), info=info,
+            triv=tuple(a[np.argsort(triv[0], kind="stable")].copy() for a in triv), n_str=0 if s is None else len(s.bytes), has_char=c is not None, out_slots=oslots.copy())
+
+    def _run_plan(self, plan, lists):
+        """the same query shape on new inputs: upload them where the recording put its inputs, re-run the bound program"""
+        for first, chars in zip(plan["in_first"], lists):
+            run = self._contiguous_run(chars)
+            self.engine.upload(first, run if run is not None else np.stack([c.ct for c in chars]).reshape(-1, self.engine.big))
+        ts, tv = plan["triv"]                         # constants the program reads: another query may have used their blocks
+        i = 0
+        while i < len(ts):                            # one call per run of consecutive slots
+            j = i + 1
+            while j < len(ts) and int(ts[j]) == int(ts[j - 1]) + 1:
+                j += 1
+            self.engine.trivial(int(ts[i]), [int(v) for v in tv[i:j]])
+            i = j
+        plan["prog"].run(rank=self.rank, world=self.world)
+        self.graph.reserve_slots(plan["n_slots"])
+        self._fresh = False
+        self.last_info = plan["info"]
+        self.plan_hits += 1
+        res = [FheAsciiChar(sk=self, graph=self.graph, slots=row.copy()) for row in plan["out_slots"]]
+        s = FheString(res[:plan["n_str"]]) if plan["n_str"] else None
+        c = res[plan["n_str"]] if plan["has_char"] else None
         return s, c
 
     def _clear(self, pattern: str):

@@ -177,6 +177,10 @@ class Graph:
         self._ck(self.lib.fhestr_graph_char_slots(self.h, _u32p(a), C.c_uint32(len(a)), _u32p(out)))
         return out
 
+    def reserve_slots(self, first_free: int):
+        """arena blocks [0, first_free) are in use by a bound program run outside this graph (plan cache)"""
+        self._ck(self.lib.fhestr_graph_reserve_slots(self.h, C.c_uint32(int(first_free))))
+
     # ---- run on the engine
     def execute(self, engine, rank: int = 0, world: int = 1):
         self._ck(self.lib.fhestr_graph_execute(self.h, engine.h, C.c_uint32(rank), C.c_uint32(world)))

@@ -198,6 +198,9 @@ int fhestr_graph_get_program(const fhestr_graph* g, fhestr_job* jobs, uint32_t* 
 int fhestr_graph_get_luts(const fhestr_graph* g, uint8_t* tables /* [n_luts][16], graph-local ids */);
 int fhestr_graph_get_trivials(const fhestr_graph* g, uint32_t* slots, uint8_t* values);
 int fhestr_graph_char_slots(const fhestr_graph* g, const uint32_t* ids, uint32_t count, uint32_t* slots /* [count][4] */);
+/* the arena blocks [0, first_free) are in use by something the graph did not record (a bound program of an earlier,
+ * identical query run again on new inputs: a plan cache above the ABI): later slots are handed out from first_free on */
+int fhestr_graph_reserve_slots(fhestr_graph* g, uint32_t first_free);
 /* run the compiled levels on the engine (registers LUTs, writes trivial outputs, shards each level over
  * `world` ranks and, when the engine has a communicator, all-gathers each level's results), then commit:
  * computed chars become inputs of whatever is recorded next */

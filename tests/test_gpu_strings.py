@@ -174,6 +174,45 @@ def test_config4_contains_find_256_chars(keys):
         assert sk.last_info.n_levels <= 10
 
 
+def test_plan_cache_reruns_a_query_shape_on_new_inputs(keys):
+    """the second call of a string method on fresh ciphertexts of the same lengths (right after reset()) re-runs the bound
+    program of the first instead of recording again: same results as Rust std on every call, results of a cached run
+    usable as operands of further ops, and plan_cache = False records every time"""
+    ck, sk, pp = keys
+    rng = random.Random(11)
+    hits0 = sk.plan_hits
+    words = ["".join(rng.choice("abcdefgh") for _ in range(12)) for _ in range(4)]
+    pats = ["cab", words[1][4:7], "hhh", words[3][9:12]]
+    for w, p in zip(words, pats):                       # contains + a follow-up op on the same inputs
+        sk.reset()
+        es, ep = ck.encrypt(w, 2, pp, sk.key), ck.encrypt_no_padding(p)
+        c = sk.contains(es, ep, pp)
+        assert ck.decrypt_char(c) == int(p in w), (w, p)
+        assert ck.decrypt_char(sk.starts_with(es, ep, pp)) == int(w.startswith(p)), (w, p)
+    assert hits0 + 3 <= sk.plan_hits <= hits0 + 4       # the first call of a shape records, the others re-run its program
+    for w in words:                                     # a string result of a cached run as the operand of another method
+        sk.reset()
+        up = sk.to_upper(ck.encrypt(w, 2, pp, sk.key), pp)
+        low = sk.to_lower(up, pp)
+        assert ck.decrypt(up) == w.upper() and ck.decrypt(low) == w
+    assert hits0 + 6 <= sk.plan_hits <= hits0 + 8
+    for a, b in (("hello", "hello"), ("hellp", "hello"), ("abcde", "abcdf")):
+        sk.reset()
+        ea, eb = ck.encrypt(a, 1, pp, sk.key), ck.encrypt(b, 1, pp, sk.key)
+        assert ck.decrypt_char(sk.eq(ea, eb, pp)) == int(a == b)
+        sk.reset()
+        ea, eb = ck.encrypt(a, 1, pp, sk.key), ck.encrypt(b, 1, pp, sk.key)
+        assert ck.decrypt_char(sk.ge(ea, eb, pp)) == int(a >= b)
+    sk.plan_cache = False
+    try:
+        h = sk.plan_hits
+        sk.reset()
+        assert ck.decrypt_char(sk.eq(ck.encrypt("hello", 1, pp, sk.key), ck.encrypt("hello", 1, pp, sk.key), pp)) == 1
+        assert sk.plan_hits == h
+    finally:
+        sk.plan_cache = True
+
+
 def test_config5_replace_1024_chars(keys):
     """BASELINE config 5: replace with encrypted from/to (4 chars each) over a 1024-char padded string"""
     ck, sk, pp = keys
