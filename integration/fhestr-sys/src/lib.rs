@@ -103,6 +103,7 @@ extern "C" {
     pub fn fhestr_graph_mark_output(g: *mut fhestr_graph, ids: *const u32, count: u32) -> c_int;
     pub fn fhestr_graph_compile(g: *mut fhestr_graph, slot_align: u32, info: *mut fhestr_graph_info) -> c_int;
     pub fn fhestr_graph_char_slots(g: *const fhestr_graph, ids: *const u32, count: u32, slots: *mut u32) -> c_int;
+    pub fn fhestr_graph_reserve_slots(g: *mut fhestr_graph, first_free: u32) -> c_int;
     pub fn fhestr_graph_execute(g: *mut fhestr_graph, e: *mut fhestr_engine, rank: u32, world: u32) -> c_int;
     // multi-GPU
     pub fn fhestr_peer_export(e: *mut fhestr_engine, arena_handle_64: *mut c_void, flags_handle_64: *mut c_void) -> c_int;
