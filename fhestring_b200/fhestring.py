@@ -209,6 +209,7 @@ class MyServerKey:
         # bound ONCE per (method, argument lengths, clear n, recording, world); the same call on new inputs re-runs
         # the bound program (upload, run) without recording anything.  plan_cache = False: always record.
         self.plan_cache = True
+        self.plan_cache_size = 32       # bound programs kept (least recently used goes first; a 138 k-PBS program is 21 MB of device memory)
         self._plans = {}
         self._fresh = True
         self.plan_hits = 0
@@ -350,8 +351,9 @@ class MyServerKey:
             lists = [self._arg_chars(a) for a in args]
             if all(len(l) for l in lists) and all(c.ct is not None and not self._mine(c) and not self._plan_value(c) for l in lists for c in l):
                 key = (method, tuple(len(l) for l in lists), bool(self.fast), int(clear_n), int(self.world))
-                plan = self._plans.get(key)
+                plan = self._plans.pop(key, None)
                 if plan is not None:
+                    self._plans[key] = plan          # dicts keep insertion order: the most recently used plan is last
                     return self._run_plan(plan, lists)
         ids = [self._ids(a) for a in args]
         rs, rc = self.graph.string_op(method, ids, fast=self.fast, clear_n=clear_n)
@@ -375,6 +377,8 @@ class MyServerKey:
         self.engine.sync()           # a failed run (peer barrier time-out) surfaces here, before anything is committed or cached
         self.graph.commit()
         oslots = self.graph.char_slots(oid)
+        while len(self._plans) >= max(1, self.plan_cache_size):
+            self._plans.pop(next(iter(self._plans)))["prog"].close()
         self._plans[key] = dict(
             prog=prog, in_first=[int(self.graph.char_slots(i[:1])[0, 0]) for i in ids], n_slots=int(info.slots_used), info=info,
             triv=tuple(a[np.argsort(triv[0], kind="stable")].copy() for a in triv), n_str=0 if s is None else len(s.bytes), has_char=c is not None, out_slots=oslots.copy())
